@@ -1,0 +1,601 @@
+// C-ABI layer (include/entreepy_b200.h): context, orchestration of the kernels, host<->device
+// staging.  Mirrors encode() (encode.zig:25) and decode() (decode.zig:13) behaviour: sizes,
+// error mapping, dry-run results and the text the reference prints.
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "et_kernels.cuh"
+
+using namespace et;
+
+struct et_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;       // context-owned stream (used when the caller passes none)
+    cudaStream_t copy_stream = nullptr;  // second stream for overlapped host copies
+    cudaEvent_t ev[6] = {};
+    // device scratch, grown on demand
+    void *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+    uint8_t *d_small = nullptr;  // fixed block: counts, tables, LUT, trie, thresholds
+    uint8_t *h_small = nullptr;  // pinned mirror of d_small + header staging
+    // bulk staging for the host-buffer entry points
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0;
+    int out_fd = 1;
+    uint64_t launches = 0;
+    float stage_ms[4] = {0, 0, 0, 0};
+    char err[512] = {0};
+};
+
+namespace {
+
+// layout of the small fixed block (device and pinned host copies share it)
+constexpr size_t kOffCounts = 0;                                    // 256 x u64
+constexpr size_t kOffPackTables = 2048;                             // narrow 1 KiB | wide 2304 B
+constexpr size_t kOffLut = 8192;                                    // 4096 x u32
+constexpr size_t kOffNodes = kOffLut + kLutSize * 4;                // kMaxTrieNodes x u32
+constexpr size_t kOffThresholds = kOffNodes + kMaxTrieNodes * 4;    // 256 x u32
+constexpr size_t kOffFlags = kOffThresholds + 1024;                 // error flags + total (16 B)
+constexpr size_t kOffHeader = kOffFlags + 64;                       // 4 KiB header staging
+constexpr size_t kSmallBytes = kOffHeader + 4096;
+constexpr size_t kMaxHeaderBytes = 4096;
+
+int fail(et_ctx *ctx, int status, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return status;
+}
+
+#define ET_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? ET_ERR_OUT_OF_MEMORY : ET_ERR_CUDA, \
+                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+    } while (0)
+
+int ensure_scratch(et_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_cap) return ET_OK;
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr;
+    ctx->scratch_cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    ET_CUDA(ctx, cudaMalloc(&ctx->d_scratch, want));
+    ctx->scratch_cap = want;
+    return ET_OK;
+}
+int ensure_bulk(et_ctx *ctx, uint8_t **buf, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return ET_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    const size_t want = ((bytes + 4096) + 255) & ~(size_t)255;
+    ET_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(buf), want));
+    *cap = want;
+    return ET_OK;
+}
+
+void fd_printf(int fd, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    const int n = vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (n > 0) (void)!write(fd, buf, (size_t)std::min<int>(n, (int)sizeof buf - 1));
+}
+
+// encode.zig:205-211: leaves in the order the explicit stack visits them (left before
+// right), i.e. ascending code order; "{c} {} - " then the code bits.
+void print_dictionary(int fd, const et_codebook &cb) {
+    std::vector<int> syms;
+    for (int s = 0; s < 256; ++s)
+        if (cb.code[s].length > 0) syms.push_back(s);
+    auto key = [&](int s) {
+        const et_code &c = cb.code[s];
+        const unsigned len = std::min<unsigned>(c.length, 32);
+        return len ? ((uint64_t)c.data << (32 - len)) & 0xFFFFFFFFull : 0ull;
+    };
+    std::sort(syms.begin(), syms.end(), [&](int a, int b) { return key(a) < key(b); });
+    for (int s : syms) {
+        std::string line;
+        line.push_back((char)s);
+        line += " " + std::to_string(s) + " - ";
+        const et_code &c = cb.code[s];
+        for (unsigned j = c.length; j > 0; --j) line.push_back(((c.data >> ((j - 1) & 31u)) & 1u) ? '1' : '0');
+        line.push_back('\n');
+        (void)!write(fd, line.data(), line.size());
+    }
+}
+
+void print_summary(double from, double to) {  // encode.zig:328-334 / decode.zig:211-217 (stderr)
+    char a[64], b[64];
+    format_file_size(a, sizeof a, from);
+    format_file_size(b, sizeof b, to);
+    fprintf(stderr, "%s => %s\n", a, b);
+}
+
+struct StageTimer {
+    et_ctx *ctx;
+    cudaStream_t s;
+    bool on;
+    void mark(int i) {
+        if (on) cudaEventRecord(ctx->ev[i], s);
+    }
+    void finish(int n_marks) {
+        if (!on) return;
+        for (int i = 0; i + 1 < n_marks && i < 4; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    }
+};
+
+// Histogram of a device buffer into host counts (blocks until the counts are on the host).
+int histogram_dev(et_ctx *ctx, const void *d_in, size_t n, uint64_t counts[256], cudaStream_t s) {
+    unsigned long long *d_counts = reinterpret_cast<unsigned long long *>(ctx->d_small + kOffCounts);
+    ET_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2048, s));
+    ET_CUDA(ctx, launch_histogram(static_cast<const uint8_t *>(d_in), n, d_counts, ctx->num_sms, s));
+    if (n) ctx->launches += 1;
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffCounts, d_counts, 2048, cudaMemcpyDeviceToHost, s));
+    ET_CUDA(ctx, cudaStreamSynchronize(s));
+    std::memcpy(counts, ctx->h_small + kOffCounts, 2048);
+    return ET_OK;
+}
+
+// Upload pack tables for `cb`; returns whether the wide kernel is needed.
+int upload_pack_tables(et_ctx *ctx, const et_codebook &cb, bool *wide, cudaStream_t s) {
+    PackTables t;
+    const int rc = make_pack_tables(cb, &t);
+    if (rc != ET_OK) return fail(ctx, rc, "code length %u cannot be emitted", cb.max_length);
+    uint8_t *h = ctx->h_small + kOffPackTables;
+    size_t bytes;
+    if (t.narrow_ok) {
+        std::memcpy(h, t.narrow, 1024);
+        bytes = 1024;
+    } else {
+        std::memcpy(h, t.wide_code, 2048);
+        std::memcpy(h + 2048, t.wide_len, 256);
+        bytes = 2304;
+    }
+    *wide = !t.narrow_ok;
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffPackTables, h, bytes, cudaMemcpyHostToDevice, s));
+    return ET_OK;
+}
+
+int pack_dev(et_ctx *ctx, const void *d_in, size_t n, const et_codebook &cb, uint32_t bit_phase, uint8_t *d_body,
+             cudaStream_t s) {
+    bool wide = false;
+    int rc = upload_pack_tables(ctx, cb, &wide, s);
+    if (rc != ET_OK) return rc;
+    const PackGeometry g = pack_geometry(d_in, n);
+    const size_t sb = pack_scratch_bytes(g.num_tiles);
+    rc = ensure_scratch(ctx, sb);
+    if (rc != ET_OK) return rc;
+    const PackScratch ps = pack_scratch_carve(ctx->d_scratch, g.num_tiles);
+    int launches = 0;
+    ET_CUDA(ctx, launch_pack(g, ctx->d_small + kOffPackTables, wide, d_body, bit_phase, ps, ctx->d_scratch, sb,
+                             ctx->num_sms, s, &launches));
+    ctx->launches += (uint64_t)launches;
+    return ET_OK;
+}
+
+struct EncodePlan {
+    et_codebook cb;
+    size_t header_len = 0, total = 0;
+};
+
+// Everything between the histogram and the pack: codebook, sizes, capacity checks.
+int plan_encode(et_ctx *ctx, const uint64_t counts[256], size_t n, size_t cap, uint32_t flags, EncodePlan *p) {
+    const int rc = et_build_codebook(counts, &p->cb);
+    if (rc != ET_OK) return fail(ctx, rc, "empty input: QueueEmpty (encode.zig:138)");
+    p->header_len = et_header_size(&p->cb);
+    p->total = p->header_len + (size_t)((p->cb.body_bits + 7) >> 3);
+    if (p->header_len > kMaxHeaderBytes) return fail(ctx, ET_ERR_UNSUPPORTED, "header of %zu bytes", p->header_len);
+    if (!(flags & ET_FLAG_NO_SCRATCH_LIMIT) && p->total > et_encode_bound(n))
+        return fail(ctx, ET_ERR_NO_SPACE, "NoSpaceLeft: %zu bytes exceed the reference scratch of 7200+n (encode.zig:253)",
+                    p->total);
+    if ((flags & ET_FLAG_WRITE_OUTPUT) && p->total > cap)
+        return fail(ctx, ET_ERR_NO_SPACE, "NoSpaceLeft: output needs %zu bytes, capacity %zu", p->total, cap);
+    return ET_OK;
+}
+
+}  // namespace
+
+// ====================================================================== context
+extern "C" int et_abi_version(void) { return ET_ABI_VERSION; }
+
+extern "C" const char *et_strerror(int status) {
+    switch (status) {
+        case ET_OK: return "ok";
+        case ET_ERR_QUEUE_EMPTY: return "QueueEmpty (empty input)";
+        case ET_ERR_NO_SPACE: return "NoSpaceLeft";
+        case ET_ERR_OUT_OF_MEMORY: return "OutOfMemory";
+        case ET_ERR_CUDA: return "CUDA error";
+        case ET_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case ET_ERR_CORRUPT: return "corrupt .et stream";
+        case ET_ERR_TOO_LARGE: return "input longer than 2^32-1 bytes";
+        case ET_ERR_UNSUPPORTED: return "unsupported";
+        case ET_ERR_INVALID_ARG: return "invalid argument";
+    }
+    return "unknown status";
+}
+
+extern "C" int et_ctx_create(int device, et_ctx **out) {
+    if (!out) return ET_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return ET_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ET_ERR_NO_DEVICE;
+    if (prop.major != 10) return ET_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    et_ctx *ctx = new (std::nothrow) et_ctx;
+    if (!ctx) return ET_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    ok = ok && cudaMalloc(reinterpret_cast<void **>(&ctx->d_small), kSmallBytes) == cudaSuccess;
+    ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_small), kSmallBytes, cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        et_ctx_destroy(ctx);
+        return ET_ERR_CUDA;
+    }
+    *out = ctx;
+    return ET_OK;
+}
+
+extern "C" void et_ctx_destroy(et_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_small) cudaFree(ctx->d_small);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    if (ctx->d_in) cudaFree(ctx->d_in);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" const char *et_last_error(const et_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+extern "C" int et_ctx_set_output_fd(et_ctx *ctx, int fd) {
+    if (!ctx) return ET_ERR_INVALID_ARG;
+    ctx->out_fd = fd;
+    return ET_OK;
+}
+extern "C" uint64_t et_ctx_kernel_launches(const et_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]) {
+    if (!ctx || !ms) return ET_ERR_INVALID_ARG;
+    std::memcpy(ms, ctx->stage_ms, sizeof ctx->stage_ms);
+    return ET_OK;
+}
+
+extern "C" int et_alloc_pinned(size_t bytes, void **out) {
+    if (!out) return ET_ERR_INVALID_ARG;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? ET_ERR_OUT_OF_MEMORY : ET_ERR_NO_DEVICE;
+    }
+    return ET_OK;
+}
+extern "C" void et_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ====================================================================== K1
+extern "C" int et_histogram_dev(et_ctx *ctx, const void *d_in, size_t n, uint64_t counts[256], void *stream) {
+    if (!ctx || !counts || (!d_in && n)) return ET_ERR_INVALID_ARG;
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return histogram_dev(ctx, d_in, n, counts, s);
+}
+
+extern "C" int et_histogram(et_ctx *ctx, const uint8_t *in, size_t n, uint64_t counts[256]) {
+    if (!ctx || !counts || (!in && n)) return ET_ERR_INVALID_ARG;
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_bulk(ctx, &ctx->d_in, &ctx->d_in_cap, n);
+    if (rc != ET_OK) return rc;
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
+    return histogram_dev(ctx, ctx->d_in, n, counts, ctx->stream);
+}
+
+// ====================================================================== encode
+extern "C" int et_encode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_out, size_t cap, size_t *out_len,
+                             uint32_t flags, void *stream) {
+    if (!ctx || !out_len || (!d_in && n)) return ET_ERR_INVALID_ARG;
+    *out_len = 0;
+    if (n == 0) return fail(ctx, ET_ERR_QUEUE_EMPTY, "empty input: QueueEmpty (encode.zig:138)");
+    if (n > 0xFFFFFFFFull) return fail(ctx, ET_ERR_TOO_LARGE, "n=%zu does not fit the 4-byte body length", n);
+    const bool write_out = (flags & ET_FLAG_WRITE_OUTPUT) != 0;
+    if (write_out && !d_out) return ET_ERR_INVALID_ARG;
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const auto t0 = std::chrono::steady_clock::now();
+    StageTimer tm{ctx, s, (flags & ET_FLAG_DEBUG) != 0};
+
+    tm.mark(0);
+    uint64_t counts[256];
+    int rc = histogram_dev(ctx, d_in, n, counts, s);  // E1
+    if (rc != ET_OK) return rc;
+    tm.mark(1);
+    EncodePlan plan;
+    rc = plan_encode(ctx, counts, n, cap, flags, &plan);  // E2-E4
+    if (rc != ET_OK) return rc;
+    if (flags & ET_FLAG_DEBUG) print_dictionary(ctx->out_fd, plan.cb);
+    if (write_out) {
+        uint8_t *h_header = ctx->h_small + kOffHeader;
+        size_t hl = 0;
+        rc = et_write_header(&plan.cb, n, h_header, kMaxHeaderBytes, &hl);  // E5
+        if (rc != ET_OK) return fail(ctx, rc, "header");
+        uint8_t *out = static_cast<uint8_t *>(d_out);
+        ET_CUDA(ctx, cudaMemcpyAsync(out, h_header, hl, cudaMemcpyHostToDevice, s));
+        tm.mark(2);
+        rc = pack_dev(ctx, d_in, n, plan.cb, 0, out + hl, s);  // E6
+        if (rc != ET_OK) return rc;
+        tm.mark(3);
+        ET_CUDA(ctx, cudaStreamSynchronize(s));
+        tm.finish(4);
+    }
+    *out_len = plan.total;  // returned even on a dry run (encode.zig:336)
+    if (flags & ET_FLAG_DEBUG) {
+        fd_printf(ctx->out_fd, "\nbits in output: %zu\n", plan.total * 8);  // encode.zig:320
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        fd_printf(ctx->out_fd, "time taken: %lldμs\n", (long long)us);  // encode.zig:27
+    }
+    return ET_OK;
+}
+
+extern "C" int et_encode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len,
+                         uint32_t flags) {
+    if (!ctx || !out_len || (!in && n)) return ET_ERR_INVALID_ARG;
+    *out_len = 0;
+    if (n == 0) return fail(ctx, ET_ERR_QUEUE_EMPTY, "empty input: QueueEmpty (encode.zig:138)");
+    if (n > 0xFFFFFFFFull) return fail(ctx, ET_ERR_TOO_LARGE, "n=%zu does not fit the 4-byte body length", n);
+    const bool write_out = (flags & ET_FLAG_WRITE_OUTPUT) != 0;
+    if (write_out && !out) return ET_ERR_INVALID_ARG;
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t s = ctx->stream;
+    int rc = ensure_bulk(ctx, &ctx->d_in, &ctx->d_in_cap, n);
+    if (rc != ET_OK) return rc;
+
+    // E1 overlapped with the upload: the input goes up in slices on copy_stream; the
+    // histogram of slice k runs on `s` while slice k+1 is still in flight.
+    unsigned long long *d_counts = reinterpret_cast<unsigned long long *>(ctx->d_small + kOffCounts);
+    ET_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 2048, s));
+    const size_t slice = (size_t)64 << 20;
+    for (size_t off = 0; off < n; off += slice) {
+        const size_t len = std::min(slice, n - off);
+        ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in + off, in + off, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        ET_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->copy_stream));
+        ET_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev[4], 0));
+        ET_CUDA(ctx, launch_histogram(ctx->d_in + off, len, d_counts, ctx->num_sms, s));
+        ctx->launches += 1;
+    }
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffCounts, d_counts, 2048, cudaMemcpyDeviceToHost, s));
+    ET_CUDA(ctx, cudaStreamSynchronize(s));
+    uint64_t counts[256];
+    std::memcpy(counts, ctx->h_small + kOffCounts, 2048);
+
+    EncodePlan plan;
+    rc = plan_encode(ctx, counts, n, cap, flags, &plan);
+    if (rc != ET_OK) return rc;
+    if (flags & ET_FLAG_DEBUG) print_dictionary(ctx->out_fd, plan.cb);
+    if (write_out) {
+        size_t hl = 0;
+        rc = et_write_header(&plan.cb, n, out, cap, &hl);  // header straight into the caller's buffer
+        if (rc != ET_OK) return fail(ctx, rc, "header");
+        const size_t body_bytes = plan.total - hl;
+        rc = ensure_bulk(ctx, &ctx->d_out, &ctx->d_out_cap, body_bytes + 16);
+        if (rc != ET_OK) return rc;
+        rc = pack_dev(ctx, ctx->d_in, n, plan.cb, 0, ctx->d_out, s);
+        if (rc != ET_OK) return rc;
+        if (body_bytes) ET_CUDA(ctx, cudaMemcpyAsync(out + hl, ctx->d_out, body_bytes, cudaMemcpyDeviceToHost, s));
+        ET_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    *out_len = plan.total;
+    if (flags & ET_FLAG_DEBUG) {
+        fd_printf(ctx->out_fd, "\nbits in output: %zu\n", plan.total * 8);
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        fd_printf(ctx->out_fd, "time taken: %lldμs\n", (long long)us);
+    }
+    if (!(flags & ET_FLAG_QUIET)) print_summary((double)n, (double)plan.total);
+    return ET_OK;
+}
+
+extern "C" int et_pack_shard_dev(et_ctx *ctx, const void *d_in, size_t n, const et_codebook *cb, uint32_t bit_phase,
+                                 void *d_out, size_t cap, size_t *out_bytes, uint64_t *bits, void *stream) {
+    if (!ctx || !cb || !d_out || bit_phase > 7 || (!d_in && n)) return ET_ERR_INVALID_ARG;
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    // the shard's bit count comes from its own histogram under the shared codebook
+    uint64_t counts[256];
+    int rc = histogram_dev(ctx, d_in, n, counts, s);
+    if (rc != ET_OK) return rc;
+    const uint64_t nbits = et_shard_bits(counts, cb);
+    const size_t bytes = (size_t)((bit_phase + nbits + 7) >> 3);
+    if (bytes > cap) return fail(ctx, ET_ERR_NO_SPACE, "shard needs %zu bytes, capacity %zu", bytes, cap);
+    if (n) {
+        rc = pack_dev(ctx, d_in, n, *cb, bit_phase, static_cast<uint8_t *>(d_out), s);
+        if (rc != ET_OK) return rc;
+        ET_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    if (out_bytes) *out_bytes = bytes;
+    if (bits) *bits = nbits;
+    return ET_OK;
+}
+
+// ====================================================================== decode
+namespace {
+
+// Decode a device-resident body.  *n_symbols = symbols the stream holds, capped at max_symbols.
+int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_dictionary &dict, uint8_t *d_out,
+               uint64_t max_symbols, uint64_t *n_symbols, cudaStream_t s) {
+    UnpackTables *t = new (std::nothrow) UnpackTables;
+    if (!t) return ET_ERR_OUT_OF_MEMORY;
+    int rc = make_unpack_tables(dict, t);
+    if (rc != ET_OK) {
+        delete t;
+        return fail(ctx, rc, rc == ET_ERR_UNSUPPORTED ? "dictionary code longer than 32 bits" : "dictionary is not a prefix code");
+    }
+    std::memcpy(ctx->h_small + kOffLut, t->lut, sizeof t->lut);
+    std::memcpy(ctx->h_small + kOffNodes, t->nodes, (size_t)t->n_nodes * 4);
+    const size_t tbl_bytes = sizeof t->lut + (size_t)t->n_nodes * 4;
+    delete t;
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffLut, ctx->h_small + kOffLut, tbl_bytes, cudaMemcpyHostToDevice, s));
+
+    const UnpackGeometry g = unpack_geometry(d_body, body_bytes);
+    const size_t sb = unpack_scratch_bytes(g.num_tiles);
+    rc = ensure_scratch(ctx, sb);
+    if (rc != ET_OK) return rc;
+    const UnpackScratch us = unpack_scratch_carve(ctx->d_scratch, g.num_tiles);
+    int launches = 0;
+    ET_CUDA(ctx, launch_unpack(g, reinterpret_cast<const uint32_t *>(ctx->d_small + kOffLut),
+                               reinterpret_cast<const uint32_t *>(ctx->d_small + kOffNodes), d_out, max_symbols, us,
+                               ctx->d_scratch, sb, ctx->num_sms, s, &launches));
+    ctx->launches += (uint64_t)launches;
+    // ticket(4) | error flags(4) | total(8)
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffFlags, ctx->d_scratch, 16, cudaMemcpyDeviceToHost, s));
+    ET_CUDA(ctx, cudaStreamSynchronize(s));
+    uint32_t flags;
+    unsigned long long total;
+    std::memcpy(&flags, ctx->h_small + kOffFlags + 4, 4);
+    std::memcpy(&total, ctx->h_small + kOffFlags + 8, 8);
+    if (flags & (kErrSeam | kErrNoConvergence))
+        return fail(ctx, ET_ERR_UNSUPPORTED, "stream did not self-synchronise (flags=%u); exhaustive path not built yet", flags);
+    if (flags & kErrInvalidCode) return fail(ctx, ET_ERR_CORRUPT, "body contains a bit pattern that is not a code");
+    *n_symbols = std::min<uint64_t>(total, max_symbols);
+    return ET_OK;
+}
+
+}  // namespace
+
+extern "C" int et_decode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_out, size_t cap, size_t *out_len,
+                             uint32_t flags, void *stream) {
+    if (!ctx || !out_len || !d_in) return ET_ERR_INVALID_ARG;
+    *out_len = 0;
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const auto t0 = std::chrono::steady_clock::now();
+    StageTimer tm{ctx, s, (flags & ET_FLAG_DEBUG) != 0};
+    tm.mark(0);
+    // D1+D2: the dictionary is parsed on the host from the first bytes of the stream
+    const size_t head = std::min(n, kMaxHeaderBytes);
+    uint8_t *h_header = ctx->h_small + kOffHeader;
+    ET_CUDA(ctx, cudaMemcpyAsync(h_header, d_in, head, cudaMemcpyDeviceToHost, s));
+    ET_CUDA(ctx, cudaStreamSynchronize(s));
+    et_dictionary dict;
+    int rc = et_parse_header(h_header, head, &dict);
+    if (rc != ET_OK) return fail(ctx, rc, "cannot parse the .et dictionary");
+    if (dict.body_offset > n) return fail(ctx, ET_ERR_CORRUPT, "dictionary runs past the end of the stream");
+    tm.mark(1);
+    if (!(flags & ET_FLAG_WRITE_OUTPUT)) return ET_OK;  // dry run: bytes_written stays 0 (decode.zig:185-188)
+    if (!d_out && cap) return ET_ERR_INVALID_ARG;
+    uint64_t produced = 0;
+    const uint64_t want = std::min<uint64_t>(dict.body_len, cap);
+    rc = unpack_dev(ctx, static_cast<const uint8_t *>(d_in) + dict.body_offset, n - dict.body_offset, dict,
+                    static_cast<uint8_t *>(d_out), want, &produced, s);  // D3
+    if (rc != ET_OK) return rc;
+    tm.mark(2);
+    tm.mark(3);
+    tm.finish(4);
+    if (produced == cap && dict.body_len > cap) return fail(ctx, ET_ERR_NO_SPACE, "NoSpaceLeft: %u symbols, capacity %zu", dict.body_len, cap);
+    *out_len = (size_t)produced;
+    if (flags & ET_FLAG_DEBUG) {
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        fd_printf(ctx->out_fd, "time taken: %lldμs\n", (long long)us);  // decode.zig:16
+    }
+    return ET_OK;
+}
+
+extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len,
+                         uint32_t flags) {
+    if (!ctx || !out_len || !in) return ET_ERR_INVALID_ARG;
+    *out_len = 0;
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t s = ctx->stream;
+    et_dictionary dict;
+    int rc = et_parse_header(in, n, &dict);  // D1+D2 straight from the caller's buffer
+    if (rc != ET_OK) return fail(ctx, rc, "cannot parse the .et dictionary");
+    if (dict.body_offset > n) return fail(ctx, ET_ERR_CORRUPT, "dictionary runs past the end of the stream");
+    const bool write_out = (flags & ET_FLAG_WRITE_OUTPUT) != 0, print_out = (flags & ET_FLAG_PRINT_OUTPUT) != 0;
+    uint64_t produced = 0;
+    if (write_out || print_out) {
+        const size_t body_bytes = n - dict.body_offset;
+        const uint64_t want = write_out ? std::min<uint64_t>(dict.body_len, cap) : dict.body_len;
+        rc = ensure_bulk(ctx, &ctx->d_in, &ctx->d_in_cap, body_bytes + 16);
+        if (rc != ET_OK) return rc;
+        rc = ensure_bulk(ctx, &ctx->d_out, &ctx->d_out_cap, want + 16);
+        if (rc != ET_OK) return rc;
+        if (body_bytes)
+            ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, in + dict.body_offset, body_bytes, cudaMemcpyHostToDevice, s));
+        rc = unpack_dev(ctx, ctx->d_in, body_bytes, dict, ctx->d_out, want, &produced, s);
+        if (rc != ET_OK) return rc;
+        if (write_out) {
+            if (produced == cap && dict.body_len > cap)
+                return fail(ctx, ET_ERR_NO_SPACE, "NoSpaceLeft: %u symbols, capacity %zu", dict.body_len, cap);
+            if (produced) ET_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, produced, cudaMemcpyDeviceToHost, s));
+            ET_CUDA(ctx, cudaStreamSynchronize(s));
+        }
+        if (print_out && produced) {  // decode.zig:189 prints every symbol to std_out
+            std::vector<uint8_t> text(produced);
+            ET_CUDA(ctx, cudaMemcpy(text.data(), ctx->d_out, produced, cudaMemcpyDeviceToHost));
+            size_t done = 0;
+            while (done < text.size()) {
+                const ssize_t w = write(ctx->out_fd, text.data() + done, text.size() - done);
+                if (w <= 0) break;
+                done += (size_t)w;
+            }
+        }
+    }
+    *out_len = write_out ? (size_t)produced : 0;  // counted only when written (decode.zig:185-188)
+    if (flags & ET_FLAG_DEBUG) {
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        fd_printf(ctx->out_fd, "time taken: %lldμs\n", (long long)us);
+    }
+    if (!(flags & ET_FLAG_QUIET)) print_summary((double)n, (double)*out_len);
+    return ET_OK;
+}
+
+extern "C" int et_unpack_shard_dev(et_ctx *ctx, const void *d_body, size_t body_bytes, const et_dictionary *dict,
+                                   uint64_t entry_bit, uint64_t bit_end, uint64_t max_symbols, void *d_out, size_t cap,
+                                   uint64_t *n_symbols, uint64_t *exit_bit, void *stream) {
+    (void)d_body; (void)body_bytes; (void)dict; (void)entry_bit; (void)bit_end; (void)max_symbols;
+    (void)d_out; (void)cap; (void)n_symbols; (void)exit_bit; (void)stream;
+    return fail(ctx, ET_ERR_UNSUPPORTED, "sharded decode is not built yet");
+}
+
+// ====================================================================== synthetic inputs
+extern "C" int et_synth_dev(et_ctx *ctx, void *d_out, size_t n, uint64_t seed, uint64_t first_index,
+                            const uint32_t thresholds[256], void *stream) {
+    if (!ctx || (!d_out && n) || !thresholds) return ET_ERR_INVALID_ARG;
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    std::memcpy(ctx->h_small + kOffThresholds, thresholds, 1024);
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffThresholds, ctx->h_small + kOffThresholds, 1024, cudaMemcpyHostToDevice, s));
+    ET_CUDA(ctx, launch_synth(static_cast<uint8_t *>(d_out), n, seed, first_index,
+                              reinterpret_cast<const uint32_t *>(ctx->d_small + kOffThresholds), s));
+    ET_CUDA(ctx, cudaStreamSynchronize(s));
+    return ET_OK;
+}

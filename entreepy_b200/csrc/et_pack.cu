@@ -1,0 +1,374 @@
+// K2 — body pack (replaces encode.zig:303-318) and the seam fix-up.
+//
+// One pass over the input: per tile of 4096 symbols
+//   (1) 16-byte load per thread, per-symbol table lookup (code,len) kept in registers,
+//   (2) block scan of per-thread bit totals, tile total published to the decoupled
+//       look-back chain, exclusive bit offset of the tile read back from it,
+//   (3) each thread shifts its 16 codes into a 64-bit accumulator and ORs whole 32-bit
+//       words into a shared-memory staging image of the tile's bitstream,
+//   (4) the staging image is byte-swapped to stream order (big-endian bit packing) and
+//       written with aligned 16-byte stores.
+// The lookup table is replicated per lane (entry (sym, lane) at word sym*32+lane) so a
+// warp-wide lookup never has a bank conflict, whatever the symbols are.
+//
+// Tiles own whole output bytes only.  The (at most two) bytes a tile shares with its
+// neighbours go to seam_head/seam_tail and are merged by seam_fixup_kernel, so the output
+// needs no pre-zeroing and no global atomics, and tiles with zero bits (the symbol the
+// reference drops when all 256 byte values occur) are handled.
+//
+// Algorithmic HBM bytes per symbol: 1 read + len/8 written (text: 1.586 B/symbol).
+#include "et_device.cuh"
+#include "et_kernels.cuh"
+
+namespace et {
+
+namespace {
+
+constexpr int kWarps = kPackThreads / 32;
+
+template <bool WIDE>
+struct PackCfg;
+template <>
+struct PackCfg<false> {
+    static constexpr int kMaxLen = (int)kNarrowMaxLen;  // 26
+    static constexpr int kTableBytes = 256 * 32 * 4;    // replicated per lane
+};
+template <>
+struct PackCfg<true> {
+    static constexpr int kMaxLen = 64;
+    static constexpr int kTableBytes = 256 * 8 + 256;  // codes + lengths, not replicated
+};
+// worst-case tile bits + up to 127 bits of alignment slack + one spare word, in uint4 units
+template <bool WIDE>
+struct StageWords {
+    static constexpr int value = (((kPackTileSyms * PackCfg<WIDE>::kMaxLen + 128 + 32) + 127) / 128) * 4;
+};
+
+struct PackArgs {
+    const uint8_t *in_aligned;
+    uint32_t misalign;
+    uint64_t v_end;
+    uint32_t num_tiles;
+    const void *tables;
+    uint8_t *out;
+    uint32_t bit_phase;
+    unsigned long long *tile_state;
+    uint8_t *seam_head;
+    uint8_t *seam_tail;
+    uint32_t *ticket;
+};
+
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += up;
+    }
+    return v;
+}
+
+// Look back over the predecessors of `tile` and return the bit offset at which it starts.
+// Called by warp 0 only.  Tile 0 publishes a prefix directly, so the walk always ends.
+__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long *state, uint32_t tile,
+                                                                uint32_t lane) {
+    unsigned long long exclusive = 0;
+    long long base = (long long)tile - 1;
+    for (;;) {
+        const long long idx = base - (long long)lane;
+        unsigned long long d;
+        uint32_t has_prefix, pending;
+        do {  // wait only for the descriptors between this tile and the nearest published prefix
+            d = idx >= 0 ? ld_relaxed_u64(state + idx) : kStatusPrefix;
+            has_prefix = __ballot_sync(0xffffffffu, (d & kStatusMask) == kStatusPrefix);
+            pending = __ballot_sync(0xffffffffu, (d & kStatusMask) == 0);
+            if (has_prefix) pending &= (1u << (__ffs((int)has_prefix) - 1)) - 1u;
+        } while (pending);
+        const uint32_t first = has_prefix ? (uint32_t)__ffs((int)has_prefix) - 1u : 31u;
+        unsigned long long v = lane <= first ? (d & ~kStatusMask) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        exclusive += v;
+        if (has_prefix) return exclusive;
+        base -= 32;
+    }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem);
+    uint8_t *table = smem + StageWords<WIDE>::value * 4;
+    __shared__ uint32_t warp_sum[kWarps];
+    __shared__ unsigned long long tile_base_sh;
+    __shared__ uint32_t tile_sh;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < StageWords<WIDE>::value; i += kPackThreads) stage[i] = 0;
+    if constexpr (!WIDE) {
+        const uint32_t *src = static_cast<const uint32_t *>(a.tables);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(table);
+        for (int i = tid; i < 256 * 32; i += kPackThreads) dst[i] = src[i >> 5];
+    } else {
+        const uint8_t *src = static_cast<const uint8_t *>(a.tables);
+        for (int i = tid; i < PackCfg<true>::kTableBytes; i += kPackThreads) table[i] = src[i];
+    }
+    const uint8_t *table_lane = table + lane * 4;
+    const unsigned long long *wide_code = reinterpret_cast<const unsigned long long *>(table);
+    const uint8_t *wide_len = table + 256 * 8;
+
+    for (;;) {
+        __syncthreads();  // staging is clean, previous tile_sh/tile_base_sh consumed
+        if (tid == 0) tile_sh = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = tile_sh;
+        if (tile >= a.num_tiles) break;
+
+        // ---- (1) load + lookup
+        const uint64_t v0 = (uint64_t)tile * kPackTileSyms + (uint64_t)tid * kPackItems;  // virtual byte index
+        const bool edge = v0 < a.misalign || v0 + kPackItems > a.v_end;
+        uint4 raw;
+        if (!edge) {
+            raw = ld_stream_v4(a.in_aligned + v0);
+        } else {
+            const long long lo = (long long)a.misalign - (long long)v0, hi = (long long)a.v_end - (long long)v0;
+            raw = (hi <= 0 || lo >= 16) ? make_uint4(0, 0, 0, 0)
+                                        : ld_partial_v4(a.in_aligned + v0, (int)max(lo, 0ll), (int)min(hi, 16ll));
+        }
+        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t ent[WIDE ? 1 : kPackItems];
+        uint32_t my_bits = 0;
+#pragma unroll
+        for (int i = 0; i < kPackItems; ++i) {
+            const uint32_t w = rw[i >> 2];
+            const int sh = 8 * (i & 3);
+            bool valid = true;
+            if (edge) valid = (v0 + i >= a.misalign) && (v0 + i < a.v_end);
+            if constexpr (!WIDE) {
+                // byte -> byte offset sym*128 into this lane's column of the table
+                const uint32_t off = sh == 0 ? ((w << 7) & 0x7f80u) : ((w >> (sh - 7)) & 0x7f80u);
+                uint32_t e = *reinterpret_cast<const uint32_t *>(table_lane + off);
+                if (!valid) e = 0;
+                ent[i] = e;
+                my_bits += e & 63u;
+            } else {
+                const uint32_t sym = (w >> sh) & 0xffu;
+                my_bits += valid ? wide_len[sym] : 0u;
+            }
+        }
+
+        // ---- (2) block scan of bit totals, look-back for the tile's bit offset
+        const uint32_t incl = warp_inclusive_scan(my_bits, lane);
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t warp_off = 0, tile_bits = 0;
+#pragma unroll
+        for (int wq = 0; wq < kWarps; ++wq) {
+            const uint32_t s = warp_sum[wq];
+            if (wq < (int)warp) warp_off += s;
+            tile_bits += s;
+        }
+        const uint32_t my_off = warp_off + incl - my_bits;
+        if (warp == 0) {
+            unsigned long long start;
+            if (tile == 0) {
+                start = a.bit_phase;
+            } else {
+                if (lane == 0) st_relaxed_u64(a.tile_state + tile, kStatusAggregate | tile_bits);
+                start = lookback_exclusive(a.tile_state, tile, lane);
+            }
+            if (lane == 0) {
+                st_relaxed_u64(a.tile_state + tile, kStatusPrefix | (start + tile_bits));
+                tile_base_sh = start;
+            }
+        }
+        __syncthreads();
+        const unsigned long long bit_begin = tile_base_sh;           // B_i: first bit of the tile in the output
+        const unsigned long long bit_end = bit_begin + tile_bits;    // E_i
+        uint8_t *first_byte = a.out + (bit_begin >> 3);              // byte holding bit B_i
+        const uint32_t align = (uint32_t)(reinterpret_cast<uintptr_t>(first_byte) & 15u);
+        uint8_t *gbase = first_byte - align;                         // staging byte k <-> gbase[k]
+        const uint32_t stage_bit0 = align * 8 + (uint32_t)(bit_begin & 7);
+
+        // ---- (3) assemble: words hold stream bits MSB-first; all stores are ORs because the
+        // first and last word of a thread are shared with its neighbours
+        {
+            uint32_t pos = stage_bit0 + my_off;
+            uint32_t fill = pos & 31u;  // bits pending in acc
+            uint32_t *wp = stage + (pos >> 5);
+            unsigned long long acc = 0;
+#pragma unroll
+            for (int i = 0; i < kPackItems; ++i) {
+                if constexpr (!WIDE) {
+                    const uint32_t len = ent[i] & 63u;
+                    acc = (acc << len) | (ent[i] >> 6);
+                    fill += len;
+                    if (fill >= 32u) {
+                        fill -= 32u;
+                        atomicOr(wp++, (uint32_t)(acc >> fill));
+                    }
+                } else {
+                    const uint32_t w = rw[i >> 2];
+                    const uint32_t sym = (w >> (8 * (i & 3))) & 0xffu;
+                    bool valid = true;
+                    if (edge) valid = (v0 + i >= a.misalign) && (v0 + i < a.v_end);
+                    const uint32_t len = valid ? wide_len[sym] : 0u;
+                    const unsigned long long code = wide_code[sym];
+                    if (len > 32u) {  // high piece first: len-32 bits
+                        const uint32_t hl = len - 32u;
+                        acc = (acc << hl) | (code >> 32);
+                        fill += hl;
+                        if (fill >= 32u) {
+                            fill -= 32u;
+                            atomicOr(wp++, (uint32_t)(acc >> fill));
+                        }
+                    }
+                    const uint32_t ll = len > 32u ? 32u : len;
+                    if (ll) {
+                        acc = (acc << ll) | (code & 0xffffffffull);
+                        fill += ll;
+                        if (fill >= 32u) {
+                            fill -= 32u;
+                            atomicOr(wp++, (uint32_t)(acc >> fill));
+                        }
+                    }
+                }
+            }
+            if (fill) atomicOr(wp, (uint32_t)(acc << (32u - fill)));
+        }
+        __syncthreads();
+
+        // ---- (4) copy out whole bytes the tile owns, park the shared ones in the seam arrays
+        {
+            const uint32_t used_bits = stage_bit0 + tile_bits;
+            const uint32_t n_chunks = (used_bits + 127u) >> 7;
+            const unsigned long long byte0 = bit_begin >> 3;
+            const unsigned long long full_lo = (bit_begin + 7) >> 3, full_hi = bit_end >> 3;  // owned bytes [lo,hi)
+            const uint32_t s_lo = (uint32_t)(full_lo - byte0) + align;                       // staging coordinates
+            const uint32_t s_hi = full_hi >= full_lo ? (uint32_t)(full_hi - byte0) + align : s_lo;
+            const bool has_head = (bit_begin & 7) != 0;
+            const bool has_tail = (bit_end & 7) != 0 && full_hi >= full_lo;
+            const uint32_t s_head = align;
+            const uint32_t s_tail = (uint32_t)(full_hi - byte0) + align;  // only meaningful when has_tail
+            if (tid == 0) {
+                if (!has_head) a.seam_head[tile] = 0;
+                if (!has_tail) a.seam_tail[tile] = 0;
+            }
+            uint4 *stage4 = reinterpret_cast<uint4 *>(stage);
+            for (uint32_t c = tid; c < n_chunks; c += kPackThreads) {
+                uint4 v = stage4[c];
+                stage4[c] = make_uint4(0, 0, 0, 0);
+                v.x = bswap32(v.x); v.y = bswap32(v.y); v.z = bswap32(v.z); v.w = bswap32(v.w);
+                const uint32_t k0 = c * 16;
+                if (k0 >= s_lo && k0 + 16 <= s_hi) {
+                    st_stream_v4(gbase + k0, v);
+                } else {
+                    const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const uint8_t byte = (uint8_t)(vw[k >> 2] >> (8 * (k & 3)));
+                        const uint32_t kk = k0 + k;
+                        if (kk >= s_lo && kk < s_hi) gbase[kk] = byte;
+                        if (has_head && kk == s_head) a.seam_head[tile] = byte;
+                        if (has_tail && kk == s_tail) a.seam_tail[tile] = byte;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One thread per tile: the byte a tile's last bits end in (when it also starts in that
+// tile) is the OR of that tile's tail and the heads of every following tile that starts
+// in the same byte.  Byte 0 of a shard that begins mid-byte has no owner; thread 0 adds it.
+__global__ void __launch_bounds__(256) seam_fixup_kernel(const unsigned long long *__restrict__ tile_state,
+                                                         const uint8_t *__restrict__ seam_head,
+                                                         const uint8_t *__restrict__ seam_tail, uint32_t num_tiles,
+                                                         uint32_t bit_phase, uint8_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_tiles) return;
+    auto end_of = [&](uint32_t j) { return tile_state[j] & ~kStatusMask; };
+    auto begin_of = [&](uint32_t j) { return j == 0 ? (unsigned long long)bit_phase : end_of(j - 1); };
+    auto merge_from = [&](unsigned long long byte, uint32_t value, uint32_t j) {
+        for (; j < num_tiles; ++j) {
+            if ((begin_of(j) >> 3) != byte) break;
+            value |= seam_head[j];
+            if ((end_of(j) >> 3) > byte) break;
+        }
+        out[byte] = (uint8_t)value;
+    };
+    const unsigned long long b = begin_of(i), e = end_of(i);
+    if ((e & 7) != 0 && ((e >> 3) << 3) >= b) merge_from(e >> 3, seam_tail[i], i + 1);
+    if (i == 0 && bit_phase != 0) merge_from(0, 0, 0);
+}
+
+}  // namespace
+
+PackGeometry pack_geometry(const void *d_in, size_t n) {
+    PackGeometry g;
+    const uintptr_t p = reinterpret_cast<uintptr_t>(d_in);
+    g.misalign = (uint32_t)(p & 15u);
+    g.in_aligned = reinterpret_cast<const uint8_t *>(p - g.misalign);
+    g.v_end = (uint64_t)g.misalign + n;
+    g.num_tiles = (uint32_t)((g.v_end + kPackTileSyms - 1) / kPackTileSyms);
+    return g;
+}
+
+size_t pack_scratch_bytes(uint32_t num_tiles) {
+    // [ticket + pad : 16][tile_state : 8*T][seam_head : T][seam_tail : T]
+    return 16 + (size_t)num_tiles * 10 + 16;
+}
+PackScratch pack_scratch_carve(void *base, uint32_t num_tiles) {
+    PackScratch s;
+    uint8_t *p = static_cast<uint8_t *>(base);
+    s.ticket = reinterpret_cast<uint32_t *>(p);
+    s.tile_state = reinterpret_cast<unsigned long long *>(p + 16);
+    s.seam_head = p + 16 + (size_t)num_tiles * 8;
+    s.seam_tail = s.seam_head + num_tiles;
+    return s;
+}
+
+cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint8_t *d_out, uint32_t bit_phase,
+                        const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
+                        cudaStream_t stream, int *launches) {
+    if (g.num_tiles == 0) return cudaSuccess;
+    cudaError_t err = cudaMemsetAsync(scratch_base, 0, scratch_bytes, stream);
+    if (err != cudaSuccess) return err;
+    PackArgs a;
+    a.in_aligned = g.in_aligned;
+    a.misalign = g.misalign;
+    a.v_end = g.v_end;
+    a.num_tiles = g.num_tiles;
+    a.tables = d_tables;
+    a.out = d_out;
+    a.bit_phase = bit_phase;
+    a.tile_state = s.tile_state;
+    a.seam_head = s.seam_head;
+    a.seam_tail = s.seam_tail;
+    a.ticket = s.ticket;
+
+    const int smem_narrow = StageWords<false>::value * 4 + PackCfg<false>::kTableBytes;
+    const int smem_wide = StageWords<true>::value * 4 + PackCfg<true>::kTableBytes;
+    err = wide ? cudaFuncSetAttribute(pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wide)
+               : cudaFuncSetAttribute(pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_narrow);
+    if (err != cudaSuccess) return err;
+    // persistent CTAs: as many as fit per SM (smem-limited), never more than there are tiles
+    const int smem = wide ? smem_wide : smem_narrow;
+    int per_sm = (227 * 1024) / (smem + 1024);
+    if (per_sm > 2048 / kPackThreads) per_sm = 2048 / kPackThreads;
+    if (per_sm < 1) per_sm = 1;
+    unsigned grid = (unsigned)num_sms * (unsigned)per_sm;
+    if (grid > g.num_tiles) grid = g.num_tiles;
+    if (wide)
+        pack_kernel<true><<<grid, kPackThreads, smem, stream>>>(a);
+    else
+        pack_kernel<false><<<grid, kPackThreads, smem, stream>>>(a);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    seam_fixup_kernel<<<(g.num_tiles + 255) / 256, 256, 0, stream>>>(s.tile_state, s.seam_head, s.seam_tail,
+                                                                    g.num_tiles, bit_phase, d_out);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+}  // namespace et

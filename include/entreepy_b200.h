@@ -1,0 +1,169 @@
+/*
+ * entreepy_b200.h — C ABI of the B200-native Huffman compress/decompress path.
+ *
+ * Drop-in boundary for typio/entreepy's codec seam.  The reference has no FFI layer; its
+ * narrowest seam is the two public functions
+ *     encode(allocator, text, out_writer, std_out, flags) !usize      (src/encode.zig:25)
+ *     decode(allocator, compressed_text, out_writer, std_out, flags) !usize (src/decode.zig:13)
+ * called from src/main.zig:202,204 and src/test.zig:15,26.  A Zig (or any other) host binds
+ * the entry points below with `extern fn` and keeps those two signatures.
+ *
+ * Conventions: plain pointers and sizes only, no exceptions cross the boundary, every entry
+ * point returns an et_status.  A context is thread-compatible (one caller at a time).
+ * There is NO CPU fallback: entry points that compute on the stream fail with
+ * ET_ERR_NO_DEVICE / ET_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef ENTREEPY_B200_H
+#define ENTREEPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ET_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ET_API __attribute__((visibility("default")))
+#else
+#define ET_API
+#endif
+
+/* ------------------------------------------------------------------ status codes */
+typedef enum et_status {
+    ET_OK = 0,
+    ET_ERR_QUEUE_EMPTY = 1,   /* empty input: QueueError.QueueEmpty, queue.zig:28 via encode.zig:138 */
+    ET_ERR_NO_SPACE = 2,      /* NoSpaceLeft: output > caller capacity or > reference scratch (encode.zig:253-254) */
+    ET_ERR_OUT_OF_MEMORY = 3, /* error.OutOfMemory (host or device allocation) */
+    ET_ERR_CUDA = 4,          /* a CUDA call failed; et_last_error() has the text */
+    ET_ERR_NO_DEVICE = 5,     /* no CUDA device / not sm_100: there is no CPU fallback */
+    ET_ERR_CORRUPT = 6,       /* .et stream cannot be parsed / is not a prefix code */
+    ET_ERR_TOO_LARGE = 7,     /* n > 2^32-1: body length field is 4 bytes (encode.zig:279, decode.zig:36-42) */
+    ET_ERR_UNSUPPORTED = 8,   /* e.g. dictionary code length > 32 on decode (decode.zig:49 holds [32]u8) */
+    ET_ERR_INVALID_ARG = 9
+} et_status;
+
+/* ------------------------------------------------------------------ flags
+ * EncodeFlags (encode.zig:9-14) / DecodeFlags (decode.zig:7-11). */
+#define ET_FLAG_WRITE_OUTPUT 0x1u /* write_output */
+#define ET_FLAG_PRINT_OUTPUT 0x2u /* print_output: decode streams the text to the output fd (decode.zig:189) */
+#define ET_FLAG_DEBUG 0x4u        /* debug: dictionary dump, "bits in output", "time taken" (encode.zig:27,205-211,320) */
+/* extensions (not in the reference) */
+#define ET_FLAG_QUIET 0x100u             /* suppress the "X => Y" stderr summary (encode.zig:334, decode.zig:217) */
+#define ET_FLAG_NO_SCRATCH_LIMIT 0x200u  /* lift the reference's 7200+n scratch bound (encode.zig:253) */
+#define ET_FLAG_VALIDATE 0x400u          /* decode: reject non-prefix / incomplete dictionaries up front */
+
+/* ------------------------------------------------------------------ code tables */
+/* Code{data:u32,length:u8}, encode.zig:141-144.  data keeps only the low 32 path bits. */
+typedef struct et_code {
+    uint32_t data;
+    uint8_t length;
+} et_code;
+
+typedef struct et_codebook {
+    et_code code[256];    /* dictionary[256], encode.zig:146; length 0 = symbol has no code */
+    uint32_t n_symbols;   /* leaves that entered the tree (symbols_length, encode.zig:79) */
+    uint32_t n_entries;   /* codes with length > 0 (encode.zig:270-273) */
+    uint32_t min_length;  /* over entries; 0 when n_entries == 0 */
+    uint32_t max_length;
+    uint64_t body_bits;   /* sum count*length: bits the body occupies before the final pad */
+} et_codebook;
+
+/* Parsed .et dictionary (decode.zig:34-141).  `in` handed to the parser is file[4..]. */
+typedef struct et_dictionary {
+    uint32_t n_entries;    /* in[0] + 1 as u8 (decode.zig:34) */
+    uint32_t body_len;     /* symbols to decode, BE u32 (decode.zig:36-42) */
+    uint64_t body_offset;  /* byte offset of the body inside `in` (decode.zig:136,156) */
+    uint8_t symbol[256];
+    uint8_t length[256];
+    uint64_t code[256];
+    uint32_t min_length, max_length;
+} et_dictionary;
+
+typedef struct et_ctx et_ctx;
+
+/* ------------------------------------------------------------------ context */
+ET_API int et_abi_version(void);
+ET_API const char *et_strerror(int status);
+/* Creates a context on CUDA device `device` (streams, device scratch, pinned staging). */
+ET_API int et_ctx_create(int device, et_ctx **out);
+ET_API void et_ctx_destroy(et_ctx *ctx);
+ET_API const char *et_last_error(const et_ctx *ctx);
+/* fd that plays the role of the reference's `std_out` argument (default 1). */
+ET_API int et_ctx_set_output_fd(et_ctx *ctx, int fd);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+ET_API uint64_t et_ctx_kernel_launches(const et_ctx *ctx);
+/* Milliseconds the last et_*_dev call spent per stage, measured with CUDA events on the
+ * launching stream: [0]=histogram [1]=host tree/tables [2]=pack or decode [3]=seam fix-up.
+ * Only filled when ET_FLAG_DEBUG was passed. */
+ET_API int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]);
+
+/* Pinned host memory for full-rate host<->device copies in et_encode/et_decode. */
+ET_API int et_alloc_pinned(size_t bytes, void **out);
+ET_API void et_free_pinned(void *p);
+
+/* ------------------------------------------------------------------ host-only steps (no GPU) */
+/* E2-E4: sort (encode.zig:54-74, incl. the saturating u8 index), two-queue tree
+ * (encode.zig:82-138, queue.zig:9-43) and code assignment (encode.zig:141-214).
+ * ET_ERR_QUEUE_EMPTY when every count is zero. */
+ET_API int et_build_codebook(const uint64_t counts[256], et_codebook *cb);
+/* E5: header bytes 0..H-1 (encode.zig:261-299): magic e7 c0 de, version 01, entries-1,
+ * n mod 2^32 BE, bit-packed (symbol,len,code) records, zero pad to a byte. */
+ET_API size_t et_header_size(const et_codebook *cb);
+ET_API int et_write_header(const et_codebook *cb, uint64_t n, uint8_t *out, size_t cap, size_t *header_len);
+/* E7: the reference's scratch size 7200 + n (encode.zig:253-254). */
+ET_API size_t et_encode_bound(size_t n);
+/* D1+D2: parse file[4..] (decode.zig:34-141). */
+ET_API int et_parse_header(const uint8_t *in_after_magic, size_t n, et_dictionary *dict);
+
+/* ------------------------------------------------------------------ E1: histogram (kernel K1) */
+/* encode.zig:43-47.  Host-buffer and device-buffer forms. `stream` is a cudaStream_t
+ * (NULL = the context's own stream). */
+ET_API int et_histogram(et_ctx *ctx, const uint8_t *in, size_t n, uint64_t counts[256]);
+ET_API int et_histogram_dev(et_ctx *ctx, const void *d_in, size_t n, uint64_t counts[256], void *stream);
+
+/* ------------------------------------------------------------------ encode / decode */
+/* encode.zig:25.  Writes the complete .et file into out[0..*out_len).  Without
+ * ET_FLAG_WRITE_OUTPUT nothing is written but *out_len is still the file size
+ * (encode.zig:319,336). */
+ET_API int et_encode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len, uint32_t flags);
+/* decode.zig:13.  `in` is file[4..] exactly as main.zig:204 / test.zig:26 pass it.
+ * *out_len = bytes written (0 on a dry run, decode.zig:187,219). */
+ET_API int et_decode(et_ctx *ctx, const uint8_t *in_after_magic, size_t n, uint8_t *out, size_t cap, size_t *out_len,
+              uint32_t flags);
+/* Same, input and output resident in device memory (no PCIe bulk copies). */
+ET_API int et_encode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_out, size_t cap, size_t *out_len, uint32_t flags,
+                  void *stream);
+ET_API int et_decode_dev(et_ctx *ctx, const void *d_in_after_magic, size_t n, void *d_out, size_t cap, size_t *out_len,
+                  uint32_t flags, void *stream);
+
+/* ------------------------------------------------------------------ sharded path */
+/* Encode shard: pack d_in[0..n) with `cb` so that its first code bit lands at bit
+ * `bit_phase` (0..7) of d_out[0]; bits before it are left zero, so the seam byte of two
+ * adjacent shards is the OR of their two copies.  *out_bytes = ceil((bit_phase+bits)/8). */
+ET_API int et_pack_shard_dev(et_ctx *ctx, const void *d_in, size_t n, const et_codebook *cb, uint32_t bit_phase,
+                      void *d_out, size_t cap, size_t *out_bytes, uint64_t *bits, void *stream);
+/* Bits a shard with these local counts occupies under `cb` (the cross-GPU scan input). */
+ET_API uint64_t et_shard_bits(const uint64_t counts[256], const et_codebook *cb);
+/* Decode shard: decode the body bit range [bit_begin, bit_end) of d_body (byte 0 of
+ * d_body is byte 0 of the body).  Step 1 resolves where the first codeword at or after
+ * bit_begin starts, given `entry_bit` = a known codeword boundary (< bit_begin, or
+ * bit_begin itself for the first shard), and counts the symbols that START inside the
+ * range; step 2 writes them to d_out[0..count).  *exit_bit = first codeword boundary
+ * >= bit_end (the next shard's entry). */
+ET_API int et_unpack_shard_dev(et_ctx *ctx, const void *d_body, size_t body_bytes, const et_dictionary *dict,
+                        uint64_t entry_bit, uint64_t bit_end, uint64_t max_symbols, void *d_out, size_t cap,
+                        uint64_t *n_symbols, uint64_t *exit_bit, void *stream);
+
+/* ------------------------------------------------------------------ synthetic inputs (bench/test utility) */
+/* out[i] = smallest s with thresholds[s] > (splitmix64(seed + first_index + i) >> 32);
+ * same definition as entreepy_b200/synth.py on the CPU. */
+ET_API int et_synth_dev(et_ctx *ctx, void *d_out, size_t n, uint64_t seed, uint64_t first_index,
+                 const uint32_t thresholds[256], void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENTREEPY_B200_H */

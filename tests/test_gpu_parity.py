@@ -1,0 +1,169 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Run with -m gpu on a B200.
+
+Bar: bit-exact.  Encode: .et bytes identical to the oracle's for the same input.  Decode: the
+original bytes (north_star), identical to the oracle's decode of the same stream.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import entreepy_b200 as et
+from conftest import FIXTURES, make_cases
+from entreepy_b200 import _abi, synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_et(data):
+    return oracle.encode(data, cap=9000 + 5 * int(np.asarray(data).size)).tobytes()
+
+
+def _flags(**kw):
+    return et.EncodeFlags(write_output=True, no_scratch_limit=True, **kw)
+
+
+# ---------------------------------------------------------------- K1
+def test_histogram_matches_oracle(codec, fixtures):
+    for name in FIXTURES:
+        assert np.array_equal(codec.histogram(fixtures[name]), oracle.histogram(fixtures[name])), name
+    for name, data in make_cases().items():
+        assert np.array_equal(codec.histogram(data), oracle.histogram(data)), name
+
+
+def test_histogram_unaligned_device_pointers(codec):
+    import torch
+
+    rng = np.random.default_rng(5)
+    host = rng.integers(0, 256, 1 << 20, dtype=np.uint8)
+    dev = torch.from_numpy(host).cuda()
+    for off, n in [(0, 1 << 20), (1, 1000), (3, 65536 + 7), (15, 17), (16, 16), (7, 1), (9, 0), (5, (1 << 20) - 5)]:
+        got = codec.histogram_dev(dev.data_ptr() + off, n)
+        assert np.array_equal(got, oracle.histogram(host[off : off + n])), (off, n)
+
+
+# ---------------------------------------------------------------- encode
+def test_encode_golden_files(codec, fixtures, golden_et, manifest):
+    for name in FIXTURES:
+        n, out = codec.encode(fixtures[name])
+        assert n == manifest[name]["et_bytes"]
+        assert hashlib.sha256(out.tobytes()).hexdigest() == manifest[name]["et_sha256"]
+        assert out.tobytes() == golden_et[name]
+
+
+def test_encode_matches_oracle_on_cases(codec):
+    for name, data in make_cases().items():
+        n, out = codec.encode(data, _flags())
+        assert out.tobytes() == _oracle_et(data), name
+
+
+def test_encode_dry_run_returns_size_only(codec, fixtures, manifest):
+    n, out = codec.encode(fixtures["nice.shakespeare.txt"], et.EncodeFlags(write_output=False))
+    assert n == 374 and out is None  # encode.zig:319,336; README.md:51
+
+
+def test_encode_empty_input_is_queue_empty(codec):
+    with pytest.raises(et.EntreepyError) as e:
+        codec.encode(b"")
+    assert e.value.name == "QueueEmpty"
+
+
+def test_encode_respects_capacity_and_reference_scratch(codec):
+    rng = np.random.default_rng(2)
+    data = rng.integers(0, 256, 50000, dtype=np.uint8)
+    with pytest.raises(et.EntreepyError) as e:
+        codec.encode(data, et.EncodeFlags(write_output=True), cap=1000)
+    assert e.value.name == "NoSpaceLeft"
+
+
+def test_encode_text_sizes_and_alignments(codec, manifest):
+    import torch
+
+    thr = synth.thresholds_from_weights(synth.text_weights(manifest["midsummer_histogram"]))
+    host = synth.generate((1 << 21) + 77, thr)
+    dev = torch.from_numpy(host).cuda()
+    out = torch.empty(host.size + 16384, dtype=torch.uint8, device="cuda")
+    for off, n, out_off in [(0, host.size, 0), (1, 100000, 3), (13, 4096 * 3 - 13, 1), (16, 4096, 15), (5, 4090, 7),
+                            (0, 1 << 20, 9)]:
+        got = codec.encode_dev(dev.data_ptr() + off, n, out.data_ptr() + out_off, out.numel() - out_off,
+                               _abi.FLAG_WRITE_OUTPUT | _abi.FLAG_NO_SCRATCH_LIMIT)
+        want = _oracle_et(host[off : off + n])
+        assert got == len(want), (off, n)
+        assert out[out_off : out_off + got].cpu().numpy().tobytes() == want, (off, n, out_off)
+
+
+def test_encode_wide_codes_fibonacci_depth_32_and_beyond(codec):
+    # depth 32 = deepest the reference represents faithfully; depth 34 exercises the
+    # truncated-code emission (encode.zig:311 shift is u5) which must still match bit for bit
+    rng = np.random.default_rng(9)
+    for depth in (27, 32, 34):
+        w = synth.fibonacci_weights(depth)
+        n = 1 << 22
+        data = synth.generate(n, synth.thresholds_from_weights(w), seed=depth)
+        # make sure every symbol occurs, rarest ones at least once, so the tree has full depth
+        data[: depth + 1] = np.arange(depth + 1, dtype=np.uint8)
+        occ = oracle.histogram(data)
+        _, length = oracle.build_dictionary(occ)
+        n_out, out = codec.encode(data, _flags())
+        assert out.tobytes() == _oracle_et(data), (depth, int(length.max()))
+
+
+# ---------------------------------------------------------------- decode
+def test_decode_golden_files(codec, fixtures, golden_et):
+    for name in FIXTURES:
+        n, out = codec.decode(golden_et[name][4:])  # file[4..] as main.zig:204
+        assert n == len(fixtures[name]) and out.tobytes() == fixtures[name], name
+
+
+def test_round_trip_like_the_reference_tests(codec, fixtures):
+    # test.zig:7-33: encode into a buffer, decode encoded[4..len], compare strings
+    for name in FIXTURES:
+        n, enc = codec.encode(fixtures[name])
+        m, dec = codec.decode(enc[4:n])
+        assert dec.tobytes() == fixtures[name]
+
+
+def test_decode_matches_oracle_on_cases(codec):
+    for name, data in make_cases().items():
+        stream = _oracle_et(data)[4:]
+        if name in ("one_byte", "single_symbol_run"):
+            with pytest.raises(et.EntreepyError):  # zero dictionary entries: nothing can decode this
+                codec.decode(stream)
+            continue
+        want = oracle.decode(stream, data.size).tobytes()
+        n, out = codec.decode(stream)
+        assert out.tobytes() == want, name
+        if name not in ("all_256_once", "all_256_uniform", "dropped_symbol_dominates"):
+            assert want == data.tobytes(), name  # lossless wherever the reference encoder is
+
+
+def test_decode_dry_run_writes_nothing(codec, golden_et):
+    n, out = codec.decode(golden_et["test.txt"][4:], et.DecodeFlags(write_output=False))
+    assert n == 0 and out is None  # decode.zig:185-188,219
+
+
+def test_decode_rejects_garbage(codec):
+    with pytest.raises(et.EntreepyError):
+        codec.decode(b"\x01\x00\x00")
+    with pytest.raises(et.EntreepyError):
+        codec.decode(bytes([1, 0, 0, 0, 9, 65, 1, 0b10000000, 66, 1]))  # second entry truncated
+
+
+def test_round_trip_text_16m_property(codec, manifest):
+    import torch
+
+    thr = synth.thresholds_from_weights(synth.text_weights(manifest["midsummer_histogram"]))
+    n = (1 << 24) + 3
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    codec.synth_dev(dev.data_ptr(), n, synth.SEED, 0, thr)
+    assert np.array_equal(dev[: 1 << 16].cpu().numpy(), synth.generate(1 << 16, thr))  # CPU twin agrees
+    enc = torch.empty(n + 8192, dtype=torch.uint8, device="cuda")
+    size = codec.encode_dev(dev.data_ptr(), n, enc.data_ptr(), enc.numel())
+    host = dev.cpu().numpy()
+    want = _oracle_et(host)
+    assert size == len(want)
+    assert hashlib.sha256(enc[:size].cpu().numpy().tobytes()).hexdigest() == hashlib.sha256(want).hexdigest()
+    dec = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    got = codec.decode_dev(enc.data_ptr() + 4, size - 4, dec.data_ptr(), n)
+    assert got == n and torch.equal(dec, dev)
