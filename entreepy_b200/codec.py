@@ -106,8 +106,12 @@ class Codec:
             self._ctx = None
             raise EntreepyError(rc, "et_ctx_create failed — a B200 (sm_100) is required, there is no CPU fallback")
         self.device = device
+        self._pinned = []
 
     def close(self):
+        for p in getattr(self, "_pinned", []):
+            self._lib.et_free_pinned(p)
+        self._pinned = []
         if getattr(self, "_ctx", None):
             self._lib.et_ctx_destroy(self._ctx)
             self._ctx = None
@@ -164,6 +168,30 @@ class Codec:
         n = ctypes.c_size_t(0)
         self._check(self._lib.et_decode(self._ctx, a.ctypes.data, a.size, out.ctypes.data, cap, ctypes.byref(n), flags.bits()))
         return n.value, (out[: n.value] if flags.write_output else None)
+
+    def pinned(self, nbytes):
+        """uint8[nbytes] view of page-locked host memory (et_alloc_pinned); freed with the Codec."""
+        p = ctypes.c_void_p()
+        rc = self._lib.et_alloc_pinned(max(int(nbytes), 1), ctypes.byref(p))
+        if rc:
+            raise EntreepyError(rc, "et_alloc_pinned")
+        self._pinned.append(p)
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(max(int(nbytes), 1),))[:nbytes]
+
+    def encode_into(self, text, out, flags=None):
+        """et_encode with caller-owned host buffers (numpy uint8, ideally from .pinned()) -> file size."""
+        flags = flags or EncodeFlags(write_output=True)
+        n = ctypes.c_size_t(0)
+        self._check(self._lib.et_encode(self._ctx, text.ctypes.data, text.size, out.ctypes.data, out.size, ctypes.byref(n), flags.bits()))
+        return n.value
+
+    def decode_into(self, et_after_magic, out, flags=None):
+        """et_decode with caller-owned host buffers -> bytes written."""
+        flags = flags or DecodeFlags(write_output=True)
+        n = ctypes.c_size_t(0)
+        self._check(self._lib.et_decode(self._ctx, et_after_magic.ctypes.data, et_after_magic.size, out.ctypes.data, out.size,
+                                        ctypes.byref(n), flags.bits()))
+        return n.value
 
     # ---- device-resident buffers (raw pointers: torch tensors' data_ptr(), cudaMalloc, ...)
     def histogram_dev(self, d_in, n, stream=None):

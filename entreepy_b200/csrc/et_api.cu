@@ -135,6 +135,7 @@ struct StageTimer {
         if (on) cudaEventRecord(ctx->ev[i], s);
     }
     void finish(int n_marks) {
+        ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = ctx->stage_ms[3] = 0.f;
         if (!on) return;
         for (int i = 0; i + 1 < n_marks && i < 4; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
     }
@@ -331,7 +332,7 @@ extern "C" int et_encode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_ou
     ET_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     const auto t0 = std::chrono::steady_clock::now();
-    StageTimer tm{ctx, s, (flags & ET_FLAG_DEBUG) != 0};
+    StageTimer tm{ctx, s, (flags & (ET_FLAG_DEBUG | ET_FLAG_TIMING)) != 0};
 
     tm.mark(0);
     uint64_t counts[256];
@@ -450,7 +451,7 @@ namespace {
 
 // Decode a device-resident body.  *n_symbols = symbols the stream holds, capped at max_symbols.
 int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_dictionary &dict, uint8_t *d_out,
-               uint64_t max_symbols, uint64_t *n_symbols, cudaStream_t s) {
+               uint64_t max_symbols, uint64_t *n_symbols, cudaStream_t s, StageTimer *tm = nullptr) {
     UnpackTables *t = new (std::nothrow) UnpackTables;
     if (!t) return ET_ERR_OUT_OF_MEMORY;
     int rc = make_unpack_tables(dict, t);
@@ -463,6 +464,7 @@ int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_d
     const size_t tbl_bytes = sizeof t->lut + (size_t)t->n_nodes * 4;
     delete t;
     ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffLut, ctx->h_small + kOffLut, tbl_bytes, cudaMemcpyHostToDevice, s));
+    if (tm) tm->mark(2);
 
     const UnpackGeometry g = unpack_geometry(d_body, body_bytes);
     const size_t sb = unpack_scratch_bytes(g.num_tiles);
@@ -497,7 +499,7 @@ extern "C" int et_decode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_ou
     ET_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     const auto t0 = std::chrono::steady_clock::now();
-    StageTimer tm{ctx, s, (flags & ET_FLAG_DEBUG) != 0};
+    StageTimer tm{ctx, s, (flags & (ET_FLAG_DEBUG | ET_FLAG_TIMING)) != 0};
     tm.mark(0);
     // D1+D2: the dictionary is parsed on the host from the first bytes of the stream
     const size_t head = std::min(n, kMaxHeaderBytes);
@@ -514,10 +516,10 @@ extern "C" int et_decode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_ou
     uint64_t produced = 0;
     const uint64_t want = std::min<uint64_t>(dict.body_len, cap);
     rc = unpack_dev(ctx, static_cast<const uint8_t *>(d_in) + dict.body_offset, n - dict.body_offset, dict,
-                    static_cast<uint8_t *>(d_out), want, &produced, s);  // D3
+                    static_cast<uint8_t *>(d_out), want, &produced, s, &tm);  // D3
     if (rc != ET_OK) return rc;
-    tm.mark(2);
     tm.mark(3);
+    ET_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
     tm.finish(4);
     if (produced == cap && dict.body_len > cap) return fail(ctx, ET_ERR_NO_SPACE, "NoSpaceLeft: %u symbols, capacity %zu", dict.body_len, cap);
     *out_len = (size_t)produced;

@@ -183,6 +183,73 @@ __device__ __forceinline__ uint32_t load_word_safe(const UnpackArgs &a, uint64_t
     return v;
 }
 
+
+// 16 bytes of subsequence g into registers as big-endian words, plus the look-ahead word
+// (first word of subsequence g+1).  Contains a __syncthreads.
+__device__ __forceinline__ void load_subseq(const UnpackArgs &a, long long g, bool active, uint32_t (&w)[5],
+                                            uint32_t *warp_sh) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (active) {
+        const uint64_t byte = (uint64_t)g * 16;
+        if (byte >= a.byte_lo && byte + 16 <= a.byte_hi) {
+            raw = ld_stream_v4(a.body_aligned + byte);
+        } else {
+            const long long lo = (long long)a.byte_lo - (long long)byte, hi = (long long)a.byte_hi - (long long)byte;
+            if (hi > 0 && lo < 16) raw = ld_partial_v4(a.body_aligned + byte, (int)max(lo, 0ll), (int)min(hi, 16ll));
+        }
+    }
+    w[0] = bswap32(raw.x); w[1] = bswap32(raw.y); w[2] = bswap32(raw.z); w[3] = bswap32(raw.w);
+    uint32_t next = __shfl_down_sync(0xffffffffu, w[0], 1);
+    __syncthreads();  // warp_sh may still be in use by the previous phase
+    if (lane == 0) warp_sh[warp] = w[0];
+    __syncthreads();
+    if (lane == 31) {
+        if (warp + 1 < (uint32_t)kWarps)
+            next = warp_sh[warp + 1];
+        else
+            next = (g + 1 >= 0 && (uint64_t)(g + 1) < a.n_subseq) ? load_word_safe(a, (uint64_t)(g + 1) * 16) : 0u;
+    }
+    w[4] = next;
+}
+
+// Final pass of a tile: every owning thread decodes its subsequence from its resolved start
+// into the staging buffer (positions from the block scan), then the block stores the
+// staged text with aligned 16-byte writes.  Tiles with more symbols than the staging
+// buffer holds go round the loop again.
+template <bool TAIL>
+__device__ __forceinline__ void write_tile(const UnpackArgs &a, const uint32_t (&w)[5], uint32_t start, int lim,
+                                           bool owned, uint32_t my_cnt, uint32_t my_off, uint32_t tile_total,
+                                           unsigned long long out_base, const uint32_t *lut_sh, uint8_t *stage,
+                                           bool *bad) {
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t chunk_lo = 0; chunk_lo < tile_total; chunk_lo += kStageBytes) {
+        const unsigned long long g0 = out_base + chunk_lo;
+        if (g0 >= a.max_symbols) break;
+        uint32_t clen = min((uint32_t)kStageBytes, tile_total - chunk_lo);
+        if (g0 + clen > a.max_symbols) clen = (uint32_t)(a.max_symbols - g0);
+        uint8_t *dst = a.out + g0;
+        const uint32_t align = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+        if (owned && my_cnt && my_off < chunk_lo + clen && my_off + my_cnt > chunk_lo) {
+            uint32_t dummy;
+            walk_subseq<TAIL, true>(w, start, lim, lut_sh, a.nodes, &dummy, stage + align, my_off - chunk_lo, clen, bad);
+        }
+        __syncthreads();
+        uint8_t *gbase = dst - align;  // staging byte k <-> gbase[k]
+        const uint32_t s_lo = align, s_hi = align + clen;
+        const uint4 *stage4 = reinterpret_cast<const uint4 *>(stage);
+        for (uint32_t c = tid; c * 16 < s_hi; c += kUnpackThreads) {
+            const uint32_t k0 = c * 16;
+            if (k0 >= s_lo && k0 + 16 <= s_hi) {
+                st_stream_v4(gbase + k0, stage4[c]);
+            } else {
+                for (uint32_t k = max(k0, s_lo); k < min(k0 + 16, s_hi); ++k) gbase[k] = stage[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <bool TAIL>
 __device__ __forceinline__ void unpack_tile(const UnpackArgs &a, uint32_t tile, const uint32_t *lut_sh,
                                             uint8_t *stage, uint32_t *exit_sh, uint32_t *warp_sh,
@@ -192,32 +259,8 @@ __device__ __forceinline__ void unpack_tile(const UnpackArgs &a, uint32_t tile, 
     const bool active = g >= 0 && (uint64_t)g < a.n_subseq;
     const bool owned = active && tid >= (uint32_t)kUnpackWarm;
 
-    // ---- load: 16 bytes per thread straight into registers, big-endian words
     uint32_t w[5];
-    {
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (active) {
-            const uint64_t byte = (uint64_t)g * 16;
-            if (byte >= a.byte_lo && byte + 16 <= a.byte_hi) {
-                raw = ld_stream_v4(a.body_aligned + byte);
-            } else {
-                const long long lo = (long long)a.byte_lo - (long long)byte, hi = (long long)a.byte_hi - (long long)byte;
-                if (hi > 0 && lo < 16) raw = ld_partial_v4(a.body_aligned + byte, (int)max(lo, 0ll), (int)min(hi, 16ll));
-            }
-        }
-        w[0] = bswap32(raw.x); w[1] = bswap32(raw.y); w[2] = bswap32(raw.z); w[3] = bswap32(raw.w);
-        // look-ahead word = first word of the next subsequence
-        uint32_t next = __shfl_down_sync(0xffffffffu, w[0], 1);
-        if (lane == 0) warp_sh[warp] = w[0];
-        __syncthreads();
-        if (lane == 31) {
-            if (warp + 1 < (uint32_t)kWarps)
-                next = warp_sh[warp + 1];
-            else
-                next = (g + 1 >= 0 && (uint64_t)(g + 1) < a.n_subseq) ? load_word_safe(a, (uint64_t)(g + 1) * 16) : 0u;
-        }
-        w[4] = next;
-    }
+    load_subseq(a, g, active, w, warp_sh);
     int lim = 0;
     if (TAIL) {
         const long long l = (long long)a.end_bit - g * (long long)kSubseqBits;
@@ -287,32 +330,8 @@ __device__ __forceinline__ void unpack_tile(const UnpackArgs &a, uint32_t tile, 
     __syncthreads();
     const unsigned long long out_base = *base_sh;
 
-    // ---- write: decode once more from the final starts into staging, then 16-byte stores
-    for (uint32_t chunk_lo = 0; chunk_lo < tile_total; chunk_lo += kStageBytes) {
-        const unsigned long long g0 = out_base + chunk_lo;
-        if (g0 >= a.max_symbols) break;
-        uint32_t clen = min((uint32_t)kStageBytes, tile_total - chunk_lo);
-        if (g0 + clen > a.max_symbols) clen = (uint32_t)(a.max_symbols - g0);
-        uint8_t *dst = a.out + g0;
-        const uint32_t align = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
-        if (owned && my_cnt && my_off < chunk_lo + clen && my_off + my_cnt > chunk_lo) {
-            uint32_t dummy;
-            walk_subseq<TAIL, true>(w, start, lim, lut_sh, a.nodes, &dummy, stage + align, my_off - chunk_lo, clen, &bad);
-        }
-        __syncthreads();
-        uint8_t *gbase = dst - align;  // staging byte k <-> gbase[k]
-        const uint32_t s_lo = align, s_hi = align + clen;
-        const uint4 *stage4 = reinterpret_cast<const uint4 *>(stage);
-        for (uint32_t c = tid; c * 16 < s_hi; c += kUnpackThreads) {
-            const uint32_t k0 = c * 16;
-            if (k0 >= s_lo && k0 + 16 <= s_hi) {
-                st_stream_v4(gbase + k0, stage4[c]);
-            } else {
-                for (uint32_t k = max(k0, s_lo); k < min(k0 + 16, s_hi); ++k) gbase[k] = stage[k];
-            }
-        }
-        __syncthreads();
-    }
+    bad = false;  // speculative rounds may legitimately have hit non-codes; only the final path counts
+    write_tile<TAIL>(a, w, start, lim, owned, my_cnt, my_off, tile_total, out_base, lut_sh, stage, &bad);
     if (bad && owned) atomicOr(a.error_flags, kErrInvalidCode);
 }
 
@@ -322,15 +341,24 @@ __global__ void __launch_bounds__(kUnpackThreads) unpack_kernel(const UnpackArgs
     __shared__ uint32_t exit_sh[kUnpackThreads];
     __shared__ uint32_t warp_sh[kWarps];
     __shared__ unsigned long long base_sh;
-    __shared__ uint32_t tile_sh;
+    __shared__ uint32_t tile_sh, abort_sh;
 
     for (int i = threadIdx.x; i < kLutSize; i += kUnpackThreads) lut_sh[i] = a.lut[i];
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) tile_sh = atomicAdd(a.ticket, 1u);
+        if (threadIdx.x == 0) {
+            tile_sh = atomicAdd(a.ticket, 1u);
+            abort_sh = ld_relaxed_u32(a.error_flags) & (kErrSeam | kErrNoConvergence);
+        }
         __syncthreads();
         const uint32_t tile = tile_sh;
         if (tile >= a.num_tiles) break;
+        if (abort_sh) {
+            // A guess was wrong somewhere: the host will rerun the stream through the chunked
+            // path.  Drain the tickets, publishing descriptors so that no look-back waits forever.
+            if (threadIdx.x == 0) st_relaxed_u64(a.tile_state + tile, kStatusPrefix);
+            continue;
+        }
         // last owned subsequence plus its 32-bit look-ahead reaches past the stream end?
         const unsigned long long reach = ((unsigned long long)tile * kUnpackOwned + kUnpackOwned) * kSubseqBits + 32;
         if (reach > a.end_bit)

@@ -54,6 +54,7 @@ typedef enum et_status {
 #define ET_FLAG_QUIET 0x100u             /* suppress the "X => Y" stderr summary (encode.zig:334, decode.zig:217) */
 #define ET_FLAG_NO_SCRATCH_LIMIT 0x200u  /* lift the reference's 7200+n scratch bound (encode.zig:253) */
 #define ET_FLAG_VALIDATE 0x400u          /* decode: reject non-prefix / incomplete dictionaries up front */
+#define ET_FLAG_TIMING 0x800u            /* *_dev calls: record per-stage CUDA events (et_ctx_last_stage_ms), print nothing */
 
 /* ------------------------------------------------------------------ code tables */
 /* Code{data:u32,length:u8}, encode.zig:141-144.  data keeps only the low 32 path bits. */
@@ -95,9 +96,11 @@ ET_API const char *et_last_error(const et_ctx *ctx);
 ET_API int et_ctx_set_output_fd(et_ctx *ctx, int fd);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 ET_API uint64_t et_ctx_kernel_launches(const et_ctx *ctx);
-/* Milliseconds the last et_*_dev call spent per stage, measured with CUDA events on the
- * launching stream: [0]=histogram [1]=host tree/tables [2]=pack or decode [3]=seam fix-up.
- * Only filled when ET_FLAG_DEBUG was passed. */
+/* Milliseconds the last et_encode_dev / et_decode_dev call spent per stage, measured with
+ * CUDA events on the launching stream.  encode: [0]=histogram kernel + 2 KiB read-back,
+ * [1]=host codebook/header, [2]=pack + seam fix-up kernels.  decode: [0]=header read-back and
+ * dictionary parse, [1]=table upload, [2]=decode kernels.  [3]=0.
+ * Only filled when ET_FLAG_TIMING or ET_FLAG_DEBUG was passed. */
 ET_API int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]);
 
 /* Pinned host memory for full-rate host<->device copies in et_encode/et_decode. */
