@@ -48,10 +48,12 @@ class DecodeFlags:  # decode.zig:7-11
     print_output: bool = False
     debug: bool = False
     quiet: bool = True
+    chunked: bool = False  # extension: force the chunked decoder (normally chosen only when the single pass gives up)
 
     def bits(self):
         return ((_abi.FLAG_WRITE_OUTPUT if self.write_output else 0) | (_abi.FLAG_PRINT_OUTPUT if self.print_output else 0)
-                | (_abi.FLAG_DEBUG if self.debug else 0) | (_abi.FLAG_QUIET if self.quiet else 0))
+                | (_abi.FLAG_DEBUG if self.debug else 0) | (_abi.FLAG_QUIET if self.quiet else 0)
+                | (_abi.FLAG_CHUNKED_DECODE if self.chunked else 0))
 
 
 def _u8(data):
@@ -131,6 +133,11 @@ class Codec:
     @property
     def kernel_launches(self):
         return int(self._lib.et_ctx_kernel_launches(self._ctx))
+
+    @property
+    def last_decode_rounds(self):
+        """Fixpoint rounds of the chunked decoder in the last decode (0: the single-pass kernel sufficed)."""
+        return int(self._lib.et_ctx_last_decode_rounds(self._ctx))
 
     def last_stage_ms(self):
         ms = (ctypes.c_float * 4)()

@@ -33,6 +33,7 @@ struct et_ctx {
     int out_fd = 1;
     uint64_t launches = 0;
     float stage_ms[4] = {0, 0, 0, 0};
+    uint32_t last_decode_rounds = 0;  // fixpoint rounds of the chunked decoder in the last decode (0 = single pass)
     char err[512] = {0};
 };
 
@@ -289,6 +290,8 @@ extern "C" int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]) {
     return ET_OK;
 }
 
+extern "C" uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx) { return ctx ? ctx->last_decode_rounds : 0; }
+
 extern "C" int et_alloc_pinned(size_t bytes, void **out) {
     if (!out) return ET_ERR_INVALID_ARG;
     *out = nullptr;
@@ -451,7 +454,7 @@ namespace {
 
 // Decode a device-resident body.  *n_symbols = symbols the stream holds, capped at max_symbols.
 int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_dictionary &dict, uint8_t *d_out,
-               uint64_t max_symbols, uint64_t *n_symbols, cudaStream_t s, StageTimer *tm = nullptr) {
+               uint64_t max_symbols, uint64_t *n_symbols, cudaStream_t s, uint32_t api_flags, StageTimer *tm = nullptr) {
     UnpackTables *t = new (std::nothrow) UnpackTables;
     if (!t) return ET_ERR_OUT_OF_MEMORY;
     int rc = make_unpack_tables(dict, t);
@@ -467,24 +470,41 @@ int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_d
     if (tm) tm->mark(2);
 
     const UnpackGeometry g = unpack_geometry(d_body, body_bytes);
-    const size_t sb = unpack_scratch_bytes(g.num_tiles);
+    const size_t sb = std::max(unpack_scratch_bytes(g.num_tiles), chunked_scratch_bytes(g.end_bit));
     rc = ensure_scratch(ctx, sb);
     if (rc != ET_OK) return rc;
-    const UnpackScratch us = unpack_scratch_carve(ctx->d_scratch, g.num_tiles);
+    const uint32_t *d_lut = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffLut);
+    const uint32_t *d_nodes = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffNodes);
+    uint32_t flags = 0;
+    unsigned long long total = 0;
+    auto read_result = [&]() -> int {  // ticket(4) | error flags(4) | total(8)
+        ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffFlags, ctx->d_scratch, 16, cudaMemcpyDeviceToHost, s));
+        ET_CUDA(ctx, cudaStreamSynchronize(s));
+        std::memcpy(&flags, ctx->h_small + kOffFlags + 4, 4);
+        std::memcpy(&total, ctx->h_small + kOffFlags + 8, 8);
+        return ET_OK;
+    };
     int launches = 0;
-    ET_CUDA(ctx, launch_unpack(g, reinterpret_cast<const uint32_t *>(ctx->d_small + kOffLut),
-                               reinterpret_cast<const uint32_t *>(ctx->d_small + kOffNodes), d_out, max_symbols, us,
-                               ctx->d_scratch, sb, ctx->num_sms, s, &launches));
+    bool chunked = (api_flags & ET_FLAG_CHUNKED_DECODE) != 0;
+    if (!chunked) {
+        const UnpackScratch us = unpack_scratch_carve(ctx->d_scratch, g.num_tiles);
+        ET_CUDA(ctx, launch_unpack(g, d_lut, d_nodes, d_out, max_symbols, us, ctx->d_scratch,
+                                   unpack_scratch_bytes(g.num_tiles), ctx->num_sms, s, &launches));
+        rc = read_result();
+        if (rc != ET_OK) return rc;
+        // a guessed start was wrong (or a tile did not settle): this stream needs the chunked decoder
+        chunked = (flags & (kErrSeam | kErrNoConvergence)) != 0;
+    }
+    ctx->last_decode_rounds = 0;
+    if (chunked) {
+        uint32_t rounds = 0;
+        ET_CUDA(ctx, launch_unpack_chunked(g, d_lut, d_nodes, d_out, max_symbols, ctx->d_scratch, sb,
+                                           reinterpret_cast<uint32_t *>(ctx->h_small + kOffFlags + 32), s, &launches, &rounds));
+        ctx->last_decode_rounds = rounds;
+        rc = read_result();
+        if (rc != ET_OK) return rc;
+    }
     ctx->launches += (uint64_t)launches;
-    // ticket(4) | error flags(4) | total(8)
-    ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffFlags, ctx->d_scratch, 16, cudaMemcpyDeviceToHost, s));
-    ET_CUDA(ctx, cudaStreamSynchronize(s));
-    uint32_t flags;
-    unsigned long long total;
-    std::memcpy(&flags, ctx->h_small + kOffFlags + 4, 4);
-    std::memcpy(&total, ctx->h_small + kOffFlags + 8, 8);
-    if (flags & (kErrSeam | kErrNoConvergence))
-        return fail(ctx, ET_ERR_UNSUPPORTED, "stream did not self-synchronise (flags=%u); exhaustive path not built yet", flags);
     if (flags & kErrInvalidCode) return fail(ctx, ET_ERR_CORRUPT, "body contains a bit pattern that is not a code");
     *n_symbols = std::min<uint64_t>(total, max_symbols);
     return ET_OK;
@@ -516,7 +536,7 @@ extern "C" int et_decode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_ou
     uint64_t produced = 0;
     const uint64_t want = std::min<uint64_t>(dict.body_len, cap);
     rc = unpack_dev(ctx, static_cast<const uint8_t *>(d_in) + dict.body_offset, n - dict.body_offset, dict,
-                    static_cast<uint8_t *>(d_out), want, &produced, s, &tm);  // D3
+                    static_cast<uint8_t *>(d_out), want, &produced, s, flags, &tm);  // D3
     if (rc != ET_OK) return rc;
     tm.mark(3);
     ET_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
@@ -552,7 +572,7 @@ extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
         if (rc != ET_OK) return rc;
         if (body_bytes)
             ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, in + dict.body_offset, body_bytes, cudaMemcpyHostToDevice, s));
-        rc = unpack_dev(ctx, ctx->d_in, body_bytes, dict, ctx->d_out, want, &produced, s);
+        rc = unpack_dev(ctx, ctx->d_in, body_bytes, dict, ctx->d_out, want, &produced, s, flags);
         if (rc != ET_OK) return rc;
         if (write_out) {
             if (produced == cap && dict.body_len > cap)

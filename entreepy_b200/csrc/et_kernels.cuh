@@ -70,6 +70,16 @@ cudaError_t launch_unpack(const UnpackGeometry &g, const uint32_t *d_lut, const 
                           uint64_t max_symbols, const UnpackScratch &s, void *scratch_base, size_t scratch_bytes,
                           int num_sms, cudaStream_t stream, int *launches);
 
+// ---------------------------------------------------------------- chunked decoder (any prefix code)
+constexpr int kChunkBytes = 1024;   // stream bytes per thread
+constexpr int kChunkThreads = 128;
+size_t chunked_scratch_bytes(uint64_t end_bit);
+// Same result contract as launch_unpack; blocks on the stream between fixpoint rounds
+// (h_flag: pinned host word).  *rounds_out = sync launches it took.
+cudaError_t launch_unpack_chunked(const UnpackGeometry &g, const uint32_t *d_lut, const uint32_t *d_nodes, uint8_t *d_out,
+                                  uint64_t max_symbols, void *scratch_base, size_t scratch_bytes, uint32_t *h_flag,
+                                  cudaStream_t stream, int *launches, uint32_t *rounds_out);
+
 // ---------------------------------------------------------------- synthetic input generator
 cudaError_t launch_synth(uint8_t *d_out, size_t n, uint64_t seed, uint64_t first_index, const uint32_t *d_thresholds,
                          cudaStream_t stream);

@@ -54,6 +54,7 @@ typedef enum et_status {
 #define ET_FLAG_QUIET 0x100u             /* suppress the "X => Y" stderr summary (encode.zig:334, decode.zig:217) */
 #define ET_FLAG_NO_SCRATCH_LIMIT 0x200u  /* lift the reference's 7200+n scratch bound (encode.zig:253) */
 #define ET_FLAG_VALIDATE 0x400u          /* decode: reject non-prefix / incomplete dictionaries up front */
+#define ET_FLAG_CHUNKED_DECODE 0x1000u    /* decode: skip the single-pass kernel, use the chunked (always-correct) one */
 #define ET_FLAG_TIMING 0x800u            /* *_dev calls: record per-stage CUDA events (et_ctx_last_stage_ms), print nothing */
 
 /* ------------------------------------------------------------------ code tables */
@@ -102,6 +103,9 @@ ET_API uint64_t et_ctx_kernel_launches(const et_ctx *ctx);
  * dictionary parse, [1]=table upload, [2]=decode kernels.  [3]=0.
  * Only filled when ET_FLAG_TIMING or ET_FLAG_DEBUG was passed. */
 ET_API int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]);
+
+/* Fixpoint rounds the chunked decoder needed in the last decode; 0 = the single-pass kernel sufficed. */
+ET_API uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx);
 
 /* Pinned host memory for full-rate host<->device copies in et_encode/et_decode. */
 ET_API int et_alloc_pinned(size_t bytes, void **out);

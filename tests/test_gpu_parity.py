@@ -167,3 +167,48 @@ def test_round_trip_text_16m_property(codec, manifest):
     dec = torch.zeros(n, dtype=torch.uint8, device="cuda")
     got = codec.decode_dev(enc.data_ptr() + 4, size - 4, dec.data_ptr(), n)
     assert got == n and torch.equal(dec, dev)
+
+
+# ---------------------------------------------------------------- chunked decoder (streams that do not re-synchronise quickly)
+def test_chunked_decoder_matches_oracle_on_all_cases(codec, fixtures, golden_et):
+    flags = et.DecodeFlags(write_output=True, chunked=True)
+    for name in FIXTURES:
+        n, out = codec.decode(golden_et[name][4:], flags)
+        assert out.tobytes() == fixtures[name], name
+        assert codec.last_decode_rounds > 0
+    for name, data in make_cases().items():
+        if name in ("one_byte", "single_symbol_run"):
+            continue
+        stream = _oracle_et(data)[4:]
+        n, out = codec.decode(stream, flags)
+        assert out.tobytes() == oracle.decode(stream, data.size).tobytes(), name
+
+
+def test_slow_synchronising_streams_fall_back_to_the_chunked_decoder(codec):
+    # 255 equiprobable symbols: 7- and 8-bit codes only; a wrong start survives for kilobytes, so the
+    # single-pass kernel's guess fails its check and the chunked decoder takes over
+    rng = np.random.default_rng(3)
+    for n in (70000, (1 << 22) + 11):
+        data = rng.integers(1, 256, n, dtype=np.uint8)
+        stream = _oracle_et(data)[4:]
+        m, out = codec.decode(stream)
+        assert m == n and out.tobytes() == data.tobytes()
+        assert codec.last_decode_rounds > 0
+    # text re-synchronises within a few symbols: single pass, no fallback
+    text = rng.choice(np.frombuffer(b"etaoin shrdlu\n,.", dtype=np.uint8), 1 << 20)
+    m, out = codec.decode(_oracle_et(text)[4:])
+    assert out.tobytes() == text.tobytes() and codec.last_decode_rounds == 0
+
+
+def test_chunked_decoder_round_trip_text_16m(codec, manifest):
+    import torch
+
+    thr = synth.thresholds_from_weights(synth.text_weights(manifest["midsummer_histogram"]))
+    n = (1 << 24) + 3
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    codec.synth_dev(dev.data_ptr(), n, synth.SEED, 0, thr)
+    enc = torch.empty(n + 8192, dtype=torch.uint8, device="cuda")
+    size = codec.encode_dev(dev.data_ptr(), n, enc.data_ptr(), enc.numel())
+    dec = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    got = codec.decode_dev(enc.data_ptr() + 4, size - 4, dec.data_ptr(), n, _abi.FLAG_WRITE_OUTPUT | _abi.FLAG_CHUNKED_DECODE)
+    assert got == n and torch.equal(dec, dev)
