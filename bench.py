@@ -237,7 +237,7 @@ def run_ours(args, rank, world):
         ms_enc = codec.last_stage_ms()
         e1.record()
         got = coder.decode(res, enc.data_ptr(), dec.data_ptr(), n, dec_flags, stream)
-        ms_dec = codec.last_stage_ms()
+        ms_dec = codec.last_stage_ms() + [codec.last_decode_rounds]
         e2.record()
         if stats is not None:
             stats.append((e0, e1, e2, ms_enc, ms_dec))
@@ -323,6 +323,7 @@ def run_ours(args, rank, world):
             "encode_frac_of_hbm": (2 * n + c_local) / 1e9 / (statistics.mean(enc_ms) / 1e3) / peak,
             "decode_frac_of_hbm": (n + c_local) / 1e9 / (statistics.mean(dec_ms) / 1e3) / peak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "verified_round_trip": verified,
+            "decode_path": "single-pass" if stats[-1][4][4] == 0 else f"chunked ({stats[-1][4][4]} fixpoint rounds)",
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

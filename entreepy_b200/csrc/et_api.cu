@@ -42,8 +42,8 @@ namespace {
 // layout of the small fixed block (device and pinned host copies share it)
 constexpr size_t kOffCounts = 0;                                    // 256 x u64
 constexpr size_t kOffPackTables = 2048;                             // narrow 1 KiB | wide 2304 B
-constexpr size_t kOffLut = 8192;                                    // 4096 x u32
-constexpr size_t kOffNodes = kOffLut + kLutSize * 4;                // kMaxTrieNodes x u32
+constexpr size_t kOffLut = 8192;                                    // clut | wlut: 2 x 4096 x u32
+constexpr size_t kOffNodes = kOffLut + 2 * kLutSize * 4;            // kMaxTrieNodes x u32
 constexpr size_t kOffThresholds = kOffNodes + kMaxTrieNodes * 4;    // 256 x u32
 constexpr size_t kOffFlags = kOffThresholds + 1024;                 // error flags + total (16 B)
 constexpr size_t kOffHeader = kOffFlags + 64;                       // 4 KiB header staging
@@ -462,18 +462,20 @@ int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_d
         delete t;
         return fail(ctx, rc, rc == ET_ERR_UNSUPPORTED ? "dictionary code longer than 32 bits" : "dictionary is not a prefix code");
     }
-    std::memcpy(ctx->h_small + kOffLut, t->lut, sizeof t->lut);
+    std::memcpy(ctx->h_small + kOffLut, t->clut, sizeof t->clut);
+    std::memcpy(ctx->h_small + kOffLut + sizeof t->clut, t->wlut, sizeof t->wlut);
     std::memcpy(ctx->h_small + kOffNodes, t->nodes, (size_t)t->n_nodes * 4);
-    const size_t tbl_bytes = sizeof t->lut + (size_t)t->n_nodes * 4;
+    const size_t tbl_bytes = sizeof t->clut + sizeof t->wlut + (size_t)t->n_nodes * 4;
     delete t;
     ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffLut, ctx->h_small + kOffLut, tbl_bytes, cudaMemcpyHostToDevice, s));
     if (tm) tm->mark(2);
 
     const UnpackGeometry g = unpack_geometry(d_body, body_bytes);
-    const size_t sb = std::max(unpack_scratch_bytes(g.num_tiles), chunked_scratch_bytes(g.end_bit));
+    const size_t sb = std::max(unpack_scratch_bytes(g.num_tiles), chunked_scratch_bytes(g));
     rc = ensure_scratch(ctx, sb);
     if (rc != ET_OK) return rc;
-    const uint32_t *d_lut = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffLut);
+    const uint32_t *d_clut = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffLut);
+    const uint32_t *d_wlut = d_clut + kLutSize;
     const uint32_t *d_nodes = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffNodes);
     uint32_t flags = 0;
     unsigned long long total = 0;
@@ -488,7 +490,7 @@ int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_d
     bool chunked = (api_flags & ET_FLAG_CHUNKED_DECODE) != 0;
     if (!chunked) {
         const UnpackScratch us = unpack_scratch_carve(ctx->d_scratch, g.num_tiles);
-        ET_CUDA(ctx, launch_unpack(g, d_lut, d_nodes, d_out, max_symbols, us, ctx->d_scratch,
+        ET_CUDA(ctx, launch_unpack(g, d_clut, d_wlut, d_nodes, d_out, max_symbols, us, ctx->d_scratch,
                                    unpack_scratch_bytes(g.num_tiles), ctx->num_sms, s, &launches));
         rc = read_result();
         if (rc != ET_OK) return rc;
@@ -498,7 +500,7 @@ int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_d
     ctx->last_decode_rounds = 0;
     if (chunked) {
         uint32_t rounds = 0;
-        ET_CUDA(ctx, launch_unpack_chunked(g, d_lut, d_nodes, d_out, max_symbols, ctx->d_scratch, sb,
+        ET_CUDA(ctx, launch_unpack_chunked(g, d_clut, d_wlut, d_nodes, d_out, max_symbols, ctx->d_scratch, sb,
                                            reinterpret_cast<uint32_t *>(ctx->h_small + kOffFlags + 32), s, &launches, &rounds));
         ctx->last_decode_rounds = rounds;
         rc = read_result();

@@ -287,12 +287,15 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
             ++cnt;
             if (pos >= (unsigned)kLutBits) break;
         }
-        uint32_t entry;
-        if (cnt == 0)
-            entry = stuck_node & 0xFFFFu;  // len0 == 0: continue in the trie (or 0xFFFF: no code)
-        else
-            entry = sym0 | (sym1 << 8) | (len0 << 16) | (len01 << 20) | (pos << 24) | (cnt << 28);
-        t->lut[idx] = entry;
+        if (cnt == 0) {
+            t->clut[idx] = kLutMarker | (kLutMarker << 16);
+            t->wlut[idx] = (stuck_node & 0xFFFFu) | (kLutMarker << 16);
+        } else {
+            const uint32_t all = pos | (cnt << 9), one = len0 | (1u << 9);
+            const uint32_t two = cnt >= 2 ? (len01 | (2u << 9)) : one;
+            t->clut[idx] = all | (one << 16);
+            t->wlut[idx] = sym0 | (sym1 << 8) | (two << 16);
+        }
     }
     return ET_OK;
 }

@@ -25,24 +25,27 @@ constexpr uint32_t kNarrowMaxLen = 26;
 int make_pack_tables(const et_codebook &cb, PackTables *t);
 
 // ---------------------------------------------------------------- decoder tables (host -> device)
-// First level: kLutBits-bit window -> packed entry.
-//   [ 7: 0] sym0      first symbol in the window
-//   [15: 8] sym1      second symbol (valid when len01 != 0)
-//   [19:16] len0      length of the first code, 1..12; 0 = code longer than the window
-//                     (or no code at all): then [15:0] is the trie node reached, 0xFFFF = invalid
-//   [23:20] len01     bits consumed by the first two codes, 0 = second does not fit
-//   [27:24] bits_all  bits consumed by every whole code that fits in the window
-//   [31:28] cnt_all   how many codes that is (1..12)
+// Two first-level tables indexed by a kLutBits-bit window of the stream.  Entries are
+// pre-packed "adds" for a walk state that keeps the bit position in bits 0-8 and a symbol
+// count (or output address) in bits 9+:   add = bits_consumed | symbols << 9.
+// kLutMarker (bit 8) instead of an add means "the first code here is longer than the window,
+// or no code at all": the fast loops stop and the generic walker takes over.
+//   clut[w]  low 16: every whole code that fits in the window (1..12 symbols)
+//            high 16: the first code only
+//   wlut[w]  low 16: sym0 | sym1 << 8          (marker: trie node reached, 0xFFFF = no such code)
+//            high 16: the first two codes if both fit, else the first
 // Second level: binary trie, node = (child1 << 16) | child0; child < 0x8000 = node index,
 // 0x8000|sym = leaf, 0xFFFF = no such code.
 constexpr int kLutBits = 12;
 constexpr int kLutSize = 1 << kLutBits;
+constexpr uint32_t kLutMarker = 0x100u;
 constexpr uint32_t kMaxTrieNodes = 8192;
 constexpr uint32_t kChildLeaf = 0x8000u;
 constexpr uint32_t kChildNone = 0xFFFFu;
 
 struct UnpackTables {
-    uint32_t lut[kLutSize];
+    uint32_t clut[kLutSize];
+    uint32_t wlut[kLutSize];
     uint32_t nodes[kMaxTrieNodes];
     uint32_t n_nodes;
     uint32_t max_length;

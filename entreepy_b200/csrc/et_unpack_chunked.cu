@@ -25,10 +25,14 @@ namespace {
 
 struct ChunkArgs {
     const uint8_t *body_aligned;
-    uint64_t first_bit, end_bit;  // stream occupies [first_bit, end_bit) of body_aligned
+    uint64_t grid_bit;            // first bit of chunk 0 (own_begin rounded down to a subsequence)
+    uint64_t own_end_bit;         // symbols that begin before this bit are decoded
+    uint64_t end_bit;             // no code may extend past this bit
     uint64_t byte_lo, byte_hi;    // readable bytes
+    uint32_t head_off;            // start of chunk 0, bits past grid_bit (true boundary or guess)
     uint32_t n_chunks;
-    const uint32_t *lut;
+    const uint32_t *clut;
+    const uint32_t *wlut;
     const uint32_t *nodes;
     uint16_t *start_off;  // [n] first codeword of the chunk, bits past the chunk's first bit
     uint16_t *exit_off;   // [n] first codeword boundary at or after the chunk's end, bits past that end
@@ -37,6 +41,7 @@ struct ChunkArgs {
     uint32_t *changed;    // [1]
     uint32_t *error_flags;
     unsigned long long *total;
+    uint32_t *entry_exit;
     uint8_t *out;
     uint64_t max_symbols;
 };
@@ -45,7 +50,7 @@ constexpr uint32_t kChunkBits = kChunkBytes * 8;
 
 __device__ __forceinline__ uint32_t trie_walk(uint32_t win, uint32_t entry, const uint32_t *__restrict__ nodes,
                                               uint32_t *sym) {
-    uint32_t node = entry & 0xFFFFu;
+    uint32_t node = entry;
     if (node == kChildNone) return 0;
     for (int b = kLutBits; b < 32; ++b) {
         const uint32_t child = (__ldg(nodes + node) >> (16 * ((win >> (31 - b)) & 1u))) & 0xFFFFu;
@@ -93,7 +98,8 @@ struct WordReader {
 // symbols at out[o..) while o < max_symbols.
 template <bool WRITE>
 __device__ __forceinline__ uint64_t walk_chunk(const ChunkArgs &a, uint64_t pos, uint64_t own_end, uint64_t hard_end,
-                                               const uint32_t *__restrict__ lut, uint32_t *count, uint64_t o, bool *bad) {
+                                               const uint32_t *__restrict__ clut, const uint32_t *__restrict__ wlut,
+                                               uint32_t *count, uint64_t o, bool *bad) {
     uint32_t n = 0;
     uint64_t wi = pos >> 5;
     WordReader rd;
@@ -107,15 +113,16 @@ __device__ __forceinline__ uint64_t walk_chunk(const ChunkArgs &a, uint64_t pos,
             lo = rd.word(a, wi + 1);
         }
         const uint32_t win = __funnelshift_l(lo, hi, (uint32_t)pos & 31u);
-        const uint32_t e = lut[win >> (32 - kLutBits)];
-        uint32_t len = (e >> 16) & 15u, sym = e & 0xFFu;
-        if (!WRITE && len != 0 && pos + kLutBits <= own_end) {  // every code in the window begins before own_end
-            pos += (e >> 24) & 15u;
-            n += e >> 28;
+        const uint32_t idx = win >> (32 - kLutBits);
+        const uint32_t c = clut[idx];
+        if (!WRITE && !(c & kLutMarker) && pos + kLutBits <= own_end) {  // every code in the window begins before own_end
+            pos += c & 0xffu;
+            n += (c & 0xffffu) >> 9;
             continue;
         }
-        if (len == 0) {
-            len = trie_walk(win, e, a.nodes, &sym);
+        uint32_t len = (c >> 16) & 0xffu, sym = wlut[idx] & 0xffu;
+        if (c & kLutMarker) {
+            len = trie_walk(win, wlut[idx] & 0xffffu, a.nodes, &sym);
             if (len == 0) {  // no code here (incomplete dictionary): same rule as the single-pass kernel
                 *bad = true;
                 pos += 1;
@@ -135,19 +142,19 @@ __device__ __forceinline__ uint64_t walk_chunk(const ChunkArgs &a, uint64_t pos,
 }
 
 __device__ __forceinline__ void chunk_bounds(const ChunkArgs &a, uint32_t c, uint64_t *begin, uint64_t *end) {
-    *begin = (uint64_t)c * kChunkBits;
+    *begin = a.grid_bit + (uint64_t)c * kChunkBits;
     const uint64_t e = *begin + kChunkBits;
-    *end = e < a.end_bit ? e : a.end_bit;
+    *end = e < a.own_end_bit ? e : a.own_end_bit;
 }
 
 __global__ void __launch_bounds__(kChunkThreads) chunk_sync_kernel(const ChunkArgs a, int round) {
-    __shared__ uint32_t lut_sh[kLutSize];
+    __shared__ uint32_t clut_sh[kLutSize];
     const uint32_t c = blockIdx.x * kChunkThreads + threadIdx.x;
     uint32_t start = 0;
     bool work = c < a.n_chunks;
     if (work) {
         if (round == 0) {
-            start = c == 0 ? (uint32_t)a.first_bit : 0u;
+            start = c == 0 ? a.head_off : 0u;
         } else if (c == 0) {
             work = false;
         } else {
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(kChunkThreads) chunk_sync_kernel(const ChunkAr
         }
     }
     if (!__syncthreads_or(work)) return;  // later rounds touch only the chunks whose start moved
-    for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) lut_sh[i] = a.lut[i];
+    for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) clut_sh[i] = a.clut[i];
     __syncthreads();
     if (!work) return;
     if (round != 0) *a.changed = 1u;
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(kChunkThreads) chunk_sync_kernel(const ChunkAr
     uint32_t cnt = 0;
     bool bad = false;
     uint64_t reached = begin + start;
-    if (reached < end) reached = walk_chunk<false>(a, reached, end, a.end_bit, lut_sh, &cnt, 0, &bad);
+    if (reached < end) reached = walk_chunk<false>(a, reached, end, a.end_bit, clut_sh, a.wlut, &cnt, 0, &bad);
     a.start_off[c] = (uint16_t)start;
     a.exit_off[c] = (uint16_t)(reached > end ? reached - end : 0);
     a.count[c] = cnt;
@@ -192,12 +199,16 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const ChunkArgs a) {
         a.prefix[i] = run;
         run += a.count[i];
     }
-    if (t == 1023) *a.total = part[1023];
+    if (t == 1023) {
+        *a.total = part[1023];
+        a.entry_exit[0] = a.start_off[0];
+        a.entry_exit[1] = a.exit_off[a.n_chunks - 1];
+    }
 }
 
 __global__ void __launch_bounds__(kChunkThreads) chunk_write_kernel(const ChunkArgs a) {
-    __shared__ uint32_t lut_sh[kLutSize];
-    for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) lut_sh[i] = a.lut[i];
+    __shared__ uint32_t clut_sh[kLutSize];
+    for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) clut_sh[i] = a.clut[i];
     __syncthreads();
     const uint32_t c = blockIdx.x * kChunkThreads + threadIdx.x;
     if (c >= a.n_chunks) return;
@@ -207,38 +218,48 @@ __global__ void __launch_bounds__(kChunkThreads) chunk_write_kernel(const ChunkA
     chunk_bounds(a, c, &begin, &end);
     uint32_t cnt = 0;
     bool bad = false;
-    if (begin + a.start_off[c] < end) walk_chunk<true>(a, begin + a.start_off[c], end, a.end_bit, lut_sh, &cnt, o, &bad);
+    if (begin + a.start_off[c] < end)
+        walk_chunk<true>(a, begin + a.start_off[c], end, a.end_bit, clut_sh, a.wlut, &cnt, o, &bad);
     if (bad) atomicOr(a.error_flags, kErrInvalidCode);
 }
 
 }  // namespace
 
-size_t chunked_scratch_bytes(uint64_t end_bit) {
-    const uint64_t n = (end_bit + kChunkBits - 1) / kChunkBits;
-    return 64 + (size_t)n * (2 + 2 + 4 + 8) + 64;
+static uint64_t chunk_count(const UnpackGeometry &g) {
+    const uint64_t grid_bit = g.own_begin_bit / kSubseqBits * kSubseqBits;
+    return g.own_end_bit > grid_bit ? (g.own_end_bit - grid_bit + kChunkBits - 1) / kChunkBits : 0;
 }
 
-cudaError_t launch_unpack_chunked(const UnpackGeometry &g, const uint32_t *d_lut, const uint32_t *d_nodes, uint8_t *d_out,
-                                  uint64_t max_symbols, void *scratch_base, size_t scratch_bytes, uint32_t *h_flag,
-                                  cudaStream_t stream, int *launches, uint32_t *rounds_out) {
+size_t chunked_scratch_bytes(const UnpackGeometry &g) { return 64 + (size_t)chunk_count(g) * (2 + 2 + 4 + 8) + 64; }
+
+cudaError_t launch_unpack_chunked(const UnpackGeometry &g, const uint32_t *d_clut, const uint32_t *d_wlut,
+                                  const uint32_t *d_nodes, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
+                                  size_t scratch_bytes, uint32_t *h_flag, cudaStream_t stream, int *launches,
+                                  uint32_t *rounds_out) {
     (void)scratch_bytes;
-    const uint64_t n64 = (g.end_bit + kChunkBits - 1) / kChunkBits;
+    const uint64_t n64 = chunk_count(g);
+    uint8_t *p = static_cast<uint8_t *>(scratch_base);
+    cudaError_t err = cudaMemsetAsync(p, 0, 64, stream);
+    if (err != cudaSuccess) return err;
     if (n64 == 0 || g.num_tiles == 0) return cudaSuccess;
     const uint32_t n = (uint32_t)n64;
-    uint8_t *p = static_cast<uint8_t *>(scratch_base);
     ChunkArgs a;
     a.body_aligned = g.body_aligned;
-    a.first_bit = g.first_bit;
+    a.grid_bit = g.own_begin_bit / kSubseqBits * kSubseqBits;
+    a.own_end_bit = g.own_end_bit;
     a.end_bit = g.end_bit;
-    a.byte_lo = g.first_bit >> 3;
-    a.byte_hi = g.end_bit >> 3;
+    a.byte_lo = g.byte_lo;
+    a.byte_hi = g.byte_hi;
+    a.head_off = (uint32_t)(g.head_bit - a.grid_bit);
     a.n_chunks = n;
-    a.lut = d_lut;
+    a.clut = d_clut;
+    a.wlut = d_wlut;
     a.nodes = d_nodes;
-    // [ticket(4) | error flags(4) | total(8) | changed(4) ...] header shared with the single-pass kernel
+    // [ticket(4) | error flags(4) | total(8) | changed(4) | pad | entry/exit(8)]: header shared with the single-pass kernel
     a.error_flags = reinterpret_cast<uint32_t *>(p + 4);
     a.total = reinterpret_cast<unsigned long long *>(p + 8);
     a.changed = reinterpret_cast<uint32_t *>(p + 16);
+    a.entry_exit = reinterpret_cast<uint32_t *>(p + 24);
     a.prefix = reinterpret_cast<unsigned long long *>(p + 64);
     a.count = reinterpret_cast<uint32_t *>(p + 64 + (size_t)n * 8);
     a.start_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)n * 12);
@@ -246,8 +267,6 @@ cudaError_t launch_unpack_chunked(const UnpackGeometry &g, const uint32_t *d_lut
     a.out = d_out;
     a.max_symbols = max_symbols;
 
-    cudaError_t err = cudaMemsetAsync(p, 0, 64, stream);
-    if (err != cudaSuccess) return err;
     const unsigned grid = (n + kChunkThreads - 1) / kChunkThreads;
     chunk_sync_kernel<<<grid, kChunkThreads, 0, stream>>>(a, 0);
     if (launches) *launches += 1;
