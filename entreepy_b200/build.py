@@ -17,7 +17,7 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libentreepy_b200.so")
 CLI = os.path.join(PKG, "bin", "entreepy")
 
-SOURCES = ["et_host.cpp", "et_hist.cu", "et_pack.cu", "et_unpack.cu", "et_unpack_chunked.cu", "et_api.cu"]
+SOURCES = ["et_host.cpp", "et_hist.cu", "et_pack.cu", "et_unpack.cu", "et_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -48,12 +48,10 @@ class DecodeFlags:  # decode.zig:7-11
     print_output: bool = False
     debug: bool = False
     quiet: bool = True
-    chunked: bool = False  # extension: force the chunked decoder (normally chosen only when the single pass gives up)
 
     def bits(self):
         return ((_abi.FLAG_WRITE_OUTPUT if self.write_output else 0) | (_abi.FLAG_PRINT_OUTPUT if self.print_output else 0)
-                | (_abi.FLAG_DEBUG if self.debug else 0) | (_abi.FLAG_QUIET if self.quiet else 0)
-                | (_abi.FLAG_CHUNKED_DECODE if self.chunked else 0))
+                | (_abi.FLAG_DEBUG if self.debug else 0) | (_abi.FLAG_QUIET if self.quiet else 0))
 
 
 def _u8(data):
@@ -136,7 +134,7 @@ class Codec:
 
     @property
     def last_decode_rounds(self):
-        """Fixpoint rounds of the chunked decoder in the last decode (0: the single-pass kernel sufficed)."""
+        """Check rounds of the last decode (2: every guessed chunk entry was right; more: fixpoint rounds were needed)."""
         return int(self._lib.et_ctx_last_decode_rounds(self._ctx))
 
     def last_stage_ms(self):

@@ -33,7 +33,7 @@ struct et_ctx {
     int out_fd = 1;
     uint64_t launches = 0;
     float stage_ms[4] = {0, 0, 0, 0};
-    uint32_t last_decode_rounds = 0;  // fixpoint rounds of the chunked decoder in the last decode (0 = single pass)
+    uint32_t last_decode_rounds = 0;  // check rounds of the last decode (2 = every guessed entry was right)
     char err[512] = {0};
 };
 
@@ -454,7 +454,7 @@ namespace {
 
 // Decode a device-resident body.  *n_symbols = symbols the stream holds, capped at max_symbols.
 int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_dictionary &dict, uint8_t *d_out,
-               uint64_t max_symbols, uint64_t *n_symbols, cudaStream_t s, uint32_t api_flags, StageTimer *tm = nullptr) {
+               uint64_t max_symbols, uint64_t *n_symbols, cudaStream_t s, StageTimer *tm = nullptr) {
     UnpackTables *t = new (std::nothrow) UnpackTables;
     if (!t) return ET_ERR_OUT_OF_MEMORY;
     int rc = make_unpack_tables(dict, t);
@@ -471,42 +471,25 @@ int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_d
     if (tm) tm->mark(2);
 
     const UnpackGeometry g = unpack_geometry(d_body, body_bytes);
-    const size_t sb = std::max(unpack_scratch_bytes(g.num_tiles), chunked_scratch_bytes(g));
-    rc = ensure_scratch(ctx, sb);
+    const uint32_t chunk_bytes = unpack_chunk_bytes(g, ctx->num_sms);
+    rc = ensure_scratch(ctx, unpack_scratch_bytes(g, chunk_bytes));
     if (rc != ET_OK) return rc;
     const uint32_t *d_clut = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffLut);
     const uint32_t *d_wlut = d_clut + kLutSize;
     const uint32_t *d_nodes = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffNodes);
+    int launches = 0;
+    uint32_t rounds = 0;
+    ET_CUDA(ctx, launch_unpack(g, chunk_bytes, d_clut, d_wlut, d_nodes, d_out, max_symbols, ctx->d_scratch,
+                               reinterpret_cast<uint32_t *>(ctx->h_small + kOffFlags + 32), s, &launches, &rounds));
+    ctx->launches += (uint64_t)launches;
+    ctx->last_decode_rounds = rounds;
+    // header of the scratch block: pad(4) | error flags(4) | symbols found(8)
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffFlags, ctx->d_scratch, 16, cudaMemcpyDeviceToHost, s));
+    ET_CUDA(ctx, cudaStreamSynchronize(s));
     uint32_t flags = 0;
     unsigned long long total = 0;
-    auto read_result = [&]() -> int {  // ticket(4) | error flags(4) | total(8)
-        ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffFlags, ctx->d_scratch, 16, cudaMemcpyDeviceToHost, s));
-        ET_CUDA(ctx, cudaStreamSynchronize(s));
-        std::memcpy(&flags, ctx->h_small + kOffFlags + 4, 4);
-        std::memcpy(&total, ctx->h_small + kOffFlags + 8, 8);
-        return ET_OK;
-    };
-    int launches = 0;
-    bool chunked = (api_flags & ET_FLAG_CHUNKED_DECODE) != 0;
-    if (!chunked) {
-        const UnpackScratch us = unpack_scratch_carve(ctx->d_scratch, g.num_tiles);
-        ET_CUDA(ctx, launch_unpack(g, d_clut, d_wlut, d_nodes, d_out, max_symbols, us, ctx->d_scratch,
-                                   unpack_scratch_bytes(g.num_tiles), ctx->num_sms, s, &launches));
-        rc = read_result();
-        if (rc != ET_OK) return rc;
-        // a guessed start was wrong (or a tile did not settle): this stream needs the chunked decoder
-        chunked = (flags & (kErrSeam | kErrNoConvergence)) != 0;
-    }
-    ctx->last_decode_rounds = 0;
-    if (chunked) {
-        uint32_t rounds = 0;
-        ET_CUDA(ctx, launch_unpack_chunked(g, d_clut, d_wlut, d_nodes, d_out, max_symbols, ctx->d_scratch, sb,
-                                           reinterpret_cast<uint32_t *>(ctx->h_small + kOffFlags + 32), s, &launches, &rounds));
-        ctx->last_decode_rounds = rounds;
-        rc = read_result();
-        if (rc != ET_OK) return rc;
-    }
-    ctx->launches += (uint64_t)launches;
+    std::memcpy(&flags, ctx->h_small + kOffFlags + 4, 4);
+    std::memcpy(&total, ctx->h_small + kOffFlags + 8, 8);
     if (flags & kErrInvalidCode) return fail(ctx, ET_ERR_CORRUPT, "body contains a bit pattern that is not a code");
     *n_symbols = std::min<uint64_t>(total, max_symbols);
     return ET_OK;
@@ -538,7 +521,7 @@ extern "C" int et_decode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_ou
     uint64_t produced = 0;
     const uint64_t want = std::min<uint64_t>(dict.body_len, cap);
     rc = unpack_dev(ctx, static_cast<const uint8_t *>(d_in) + dict.body_offset, n - dict.body_offset, dict,
-                    static_cast<uint8_t *>(d_out), want, &produced, s, flags, &tm);  // D3
+                    static_cast<uint8_t *>(d_out), want, &produced, s, &tm);  // D3
     if (rc != ET_OK) return rc;
     tm.mark(3);
     ET_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
@@ -574,7 +557,7 @@ extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
         if (rc != ET_OK) return rc;
         if (body_bytes)
             ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, in + dict.body_offset, body_bytes, cudaMemcpyHostToDevice, s));
-        rc = unpack_dev(ctx, ctx->d_in, body_bytes, dict, ctx->d_out, want, &produced, s, flags);
+        rc = unpack_dev(ctx, ctx->d_in, body_bytes, dict, ctx->d_out, want, &produced, s);
         if (rc != ET_OK) return rc;
         if (write_out) {
             if (produced == cap && dict.body_len > cap)

@@ -40,14 +40,11 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
                         cudaStream_t stream, int *launches);
 
-// ---------------------------------------------------------------- K3-K5 (self-synchronising decoder)
-constexpr int kUnpackThreads = 256;  // subsequences per tile, warm-up included
-constexpr int kUnpackWarm = 8;       // leading subsequences re-decoded from the previous tile
-constexpr int kUnpackOwned = kUnpackThreads - kUnpackWarm;
-constexpr int kSubseqBits = 128;
-constexpr int kUnpackStageBytes = 12288;  // text of one tile staged in shared memory (avg code >= 2.6 bits)
+// ---------------------------------------------------------------- K3-K5 (chunked self-synchronising decoder)
+constexpr int kSubseqBits = 128;    // a piece: the unit the stream is read in (one 16-byte load)
+constexpr int kChunkThreads = 256;  // chunks per CTA
 
-// Where the stream sits relative to the 16-byte grid the subsequences are cut on.  All bit
+// Where the stream sits relative to the 16-byte grid the pieces are cut on.  All bit
 // positions are relative to body_aligned.
 struct UnpackGeometry {
     const uint8_t *body_aligned;  // 16-byte aligned base
@@ -55,43 +52,28 @@ struct UnpackGeometry {
     uint64_t own_begin_bit;       // symbols that begin in [own_begin_bit, own_end_bit) are decoded
     uint64_t own_end_bit;
     uint64_t end_bit;             // no code may extend past this bit (end of the stream / of the readable range)
-    bool head_known;              // head_bit is a true codeword boundary (else the first start is a guess)
+    bool head_known;              // head_bit is a true codeword boundary (else the first entry is a guess)
     uint64_t head_bit;
-    uint32_t num_tiles;
 };
 UnpackGeometry unpack_geometry(const void *d_body, size_t body_bytes);
 // A shard: d_range 16-byte aligned, own_begin_byte a multiple of 16, own_end_byte a multiple of 16
-// unless the stream ends there; range_bytes >= own_end_byte + 16 unless the stream ends there.
+// unless the stream ends there; range_bytes >= own_end_byte + 32 unless the stream ends there.
+// head_bit < 0: the first codeword boundary is unknown (found by run-up from the bytes before own_begin_byte).
 UnpackGeometry unpack_geometry_shard(const void *d_range, size_t range_bytes, size_t own_begin_byte, size_t own_end_byte,
                                      long long head_bit);
 
-struct UnpackScratch {
-    unsigned long long *tile_state;  // [num_tiles]
-    uint32_t *ticket;                // [1]
-    uint32_t *error_flags;           // [1] bit0 seam mismatch, bit1 invalid code, bit2 no convergence
-    unsigned long long *total;       // [1] symbols found
-    uint32_t *entry_exit;            // [2] start used by the first owned subsequence / exit of the last one (bits past it)
-};
-size_t unpack_scratch_bytes(uint32_t num_tiles);
-UnpackScratch unpack_scratch_carve(void *base, uint32_t num_tiles);
+constexpr uint32_t kErrInvalidCode = 2u;
 
-constexpr uint32_t kErrSeam = 1u, kErrInvalidCode = 2u, kErrNoConvergence = 4u;
-
-// d_clut/d_wlut: kLutSize x u32 each, d_nodes: trie.  Writes min(total, max_symbols) bytes to d_out.
-cudaError_t launch_unpack(const UnpackGeometry &g, const uint32_t *d_clut, const uint32_t *d_wlut, const uint32_t *d_nodes,
-                          uint8_t *d_out, uint64_t max_symbols, const UnpackScratch &s, void *scratch_base,
-                          size_t scratch_bytes, int num_sms, cudaStream_t stream, int *launches);
-
-// ---------------------------------------------------------------- chunked decoder (any prefix code)
-constexpr int kChunkBytes = 1024;   // stream bytes per thread
-constexpr int kChunkThreads = 128;
-size_t chunked_scratch_bytes(const UnpackGeometry &g);
-// Same result contract as launch_unpack; blocks on the stream between fixpoint rounds
-// (h_flag: pinned host word).  *rounds_out = sync launches it took.
-cudaError_t launch_unpack_chunked(const UnpackGeometry &g, const uint32_t *d_clut, const uint32_t *d_wlut,
-                                  const uint32_t *d_nodes, uint8_t *d_out,
-                                  uint64_t max_symbols, void *scratch_base, size_t scratch_bytes, uint32_t *h_flag,
-                                  cudaStream_t stream, int *launches, uint32_t *rounds_out);
+// Chunk size for this stream (bytes per thread) and the device scratch the decoder needs.
+uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms);
+size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes);
+// Scratch header after the call: [4] error flags (u32), [8] symbols found (u64), [24] entry used
+// by the first chunk, [28] exit of the last chunk (u32 bits).  Writes min(total, max_symbols)
+// bytes to d_out.  Blocks on the stream between check rounds (h_flag: pinned host word).
+// *rounds_out = check rounds it took (2 = the guess was right everywhere).
+cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
+                          const uint32_t *d_nodes, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
+                          uint32_t *h_flag, cudaStream_t stream, int *launches, uint32_t *rounds_out);
 
 // ---------------------------------------------------------------- synthetic input generator
 cudaError_t launch_synth(uint8_t *d_out, size_t n, uint64_t seed, uint64_t first_index, const uint32_t *d_thresholds,

@@ -54,7 +54,6 @@ typedef enum et_status {
 #define ET_FLAG_QUIET 0x100u             /* suppress the "X => Y" stderr summary (encode.zig:334, decode.zig:217) */
 #define ET_FLAG_NO_SCRATCH_LIMIT 0x200u  /* lift the reference's 7200+n scratch bound (encode.zig:253) */
 #define ET_FLAG_VALIDATE 0x400u          /* decode: reject non-prefix / incomplete dictionaries up front */
-#define ET_FLAG_CHUNKED_DECODE 0x1000u    /* decode: skip the single-pass kernel, use the chunked (always-correct) one */
 #define ET_FLAG_TIMING 0x800u            /* *_dev calls: record per-stage CUDA events (et_ctx_last_stage_ms), print nothing */
 
 /* ------------------------------------------------------------------ code tables */
@@ -104,7 +103,8 @@ ET_API uint64_t et_ctx_kernel_launches(const et_ctx *ctx);
  * Only filled when ET_FLAG_TIMING or ET_FLAG_DEBUG was passed. */
 ET_API int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]);
 
-/* Fixpoint rounds the chunked decoder needed in the last decode; 0 = the single-pass kernel sufficed. */
+/* Check rounds of the last decode: 2 = every chunk's guessed entry was a true codeword boundary
+ * (self-synchronising streams); more = that many fixpoint rounds were needed (slowly synchronising codes). */
 ET_API uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx);
 
 /* Pinned host memory for full-rate host<->device copies in et_encode/et_decode. */
