@@ -41,7 +41,7 @@ namespace {
 
 // layout of the small fixed block (device and pinned host copies share it)
 constexpr size_t kOffCounts = 0;                                    // 256 x u64
-constexpr size_t kOffPackTables = 2048;                             // narrow 1 KiB | wide 2304 B
+constexpr size_t kOffPackTables = 2048;                             // narrow 2 KiB | wide 2304 B
 constexpr size_t kOffLut = 8192;                                    // clut | wlut: 2 x 4096 x u32
 constexpr size_t kOffNodes = kOffLut + 2 * kLutSize * 4;            // kMaxTrieNodes x u32
 constexpr size_t kOffThresholds = kOffNodes + kMaxTrieNodes * 4;    // 256 x u32
@@ -162,8 +162,8 @@ int upload_pack_tables(et_ctx *ctx, const et_codebook &cb, bool *wide, cudaStrea
     uint8_t *h = ctx->h_small + kOffPackTables;
     size_t bytes;
     if (t.narrow_ok) {
-        std::memcpy(h, t.narrow, 1024);
-        bytes = 1024;
+        std::memcpy(h, t.narrow, 2048);
+        bytes = 2048;
     } else {
         std::memcpy(h, t.wide_code, 2048);
         std::memcpy(h + 2048, t.wide_len, 256);

@@ -216,7 +216,8 @@ int make_pack_tables(const et_codebook &cb, PackTables *t) {
             emitted = ((uint64_t)(len == 64 ? c.data : (c.data & ((1u << (len - 32)) - 1u))) << 32) | c.data;
         t->wide_code[s] = emitted;
         t->wide_len[s] = (uint8_t)len;
-        t->narrow[s] = t->narrow_ok ? (uint32_t)((emitted << 6) | len) : 0u;
+        t->narrow[s][0] = t->narrow_ok ? (uint32_t)emitted : 0u;
+        t->narrow[s][1] = t->narrow_ok ? len : 0u;
     }
     return ET_OK;
 }

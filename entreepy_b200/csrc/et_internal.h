@@ -14,13 +14,13 @@ namespace et {
 // itself; for 32 < length <= 64 it is the low (length-32) bits of data followed by all 32
 // bits of data (the reference's truncation artefact) — reproduced bit for bit.
 struct PackTables {
-    uint32_t narrow[256];  // (emitted << 6) | length, valid when max_length <= kNarrowMaxLen
+    uint32_t narrow[256][2];  // {emitted bits, length}, valid when max_length <= kNarrowMaxLen
     uint64_t wide_code[256];
     uint8_t wide_len[256];
     uint32_t max_length;
     bool narrow_ok;
 };
-constexpr uint32_t kNarrowMaxLen = 26;
+constexpr uint32_t kNarrowMaxLen = 32;
 
 int make_pack_tables(const et_codebook &cb, PackTables *t);
 

@@ -27,15 +27,17 @@ PackGeometry pack_geometry(const void *d_in, size_t n);
 
 // Device scratch the pack kernels need for `num_tiles` tiles.
 struct PackScratch {
-    unsigned long long *tile_state;  // [num_tiles] decoupled-lookback descriptors
-    uint8_t *seam_head;              // [num_tiles]
-    uint8_t *seam_tail;              // [num_tiles]
-    uint32_t *ticket;                // [1]
+    unsigned long long *tile_state;   // [num_tiles] last bit + 1 of each tile (wide kernel: look-back descriptors)
+    unsigned long long *group_prefix; // [ceil(num_tiles / 256)] bits before each group of tiles
+    uint32_t *tile_bits;              // [num_tiles]
+    uint8_t *seam_head;               // [num_tiles]
+    uint8_t *seam_tail;               // [num_tiles]
+    uint32_t *ticket;                 // [1] (wide kernel)
 };
 size_t pack_scratch_bytes(uint32_t num_tiles);
 PackScratch pack_scratch_carve(void *base, uint32_t num_tiles);
 
-// d_tables: narrow -> 256 x u32; wide -> 256 x u64 codes followed by 256 x u8 lengths.
+// d_tables: narrow -> 256 x {code, len} (u32 pairs); wide -> 256 x u64 codes followed by 256 x u8 lengths.
 cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint8_t *d_out, uint32_t bit_phase,
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
                         cudaStream_t stream, int *launches);

@@ -1,15 +1,23 @@
 // K2 — body pack (replaces encode.zig:303-318) and the seam fix-up.
 //
-// One pass over the input: per tile of 4096 symbols
-//   (1) 16-byte load per thread, per-symbol table lookup (code,len) kept in registers,
-//   (2) block scan of per-thread bit totals, tile total published to the decoupled
-//       look-back chain, exclusive bit offset of the tile read back from it,
-//   (3) each thread shifts its 16 codes into a 64-bit accumulator and ORs whole 32-bit
-//       words into a shared-memory staging image of the tile's bitstream,
-//   (4) the staging image is byte-swapped to stream order (big-endian bit packing) and
-//       written with aligned 16-byte stores.
-// The lookup table is replicated per lane (entry (sym, lane) at word sym*32+lane) so a
-// warp-wide lookup never has a bank conflict, whatever the symbols are.
+// One pass over the input, per tile of 4096 symbols (256 threads x one 16-byte load):
+//   (1) per-symbol table lookup (code,len); adjacent symbols are fused into PAIRS
+//       ((code_a << len_b) | code_b, len_a + len_b) kept in registers,
+//   (2) block scan of per-thread bit totals; the tile total goes to the decoupled look-back
+//       chain, which returns the tile's bit offset in the output,
+//   (3) each thread shifts its 8 pairs into a 64-bit accumulator and ORs whole 32-bit words
+//       into a shared-memory image of the tile's bitstream at TILE-RELATIVE positions, so
+//       the assembly does not wait for the look-back,
+//   (4) the image is funnel-shifted to the tile's final bit position, byte-swapped to stream
+//       order (big-endian bit packing) and written with aligned 16-byte stores.
+// The lookup table is replicated for 16 lanes (entry (sym, lane & 15) at sym*128 + lane*8):
+// a 64-bit shared load is served half a warp at a time, so no lookup ever has a bank conflict
+// whatever the symbols are.
+//
+// The fast path needs every pair to fit 32 bits (always, in practice: a code longer than 16
+// bits occurs less than once in 2^16 symbols) and a tile that lies wholly inside the input;
+// any other tile takes the per-symbol path.  Codes longer than 32 bits (where the reference
+// itself emits truncated paths) use the wide kernel further down.
 //
 // Tiles own whole output bytes only.  The (at most two) bytes a tile shares with its
 // neighbours go to seam_head/seam_tail and are merged by seam_fixup_kernel, so the output
@@ -28,11 +36,6 @@ constexpr int kWarps = kPackThreads / 32;
 
 template <bool WIDE>
 struct PackCfg;
-template <>
-struct PackCfg<false> {
-    static constexpr int kMaxLen = (int)kNarrowMaxLen;  // 26
-    static constexpr int kTableBytes = 256 * 32 * 4;    // replicated per lane
-};
 template <>
 struct PackCfg<true> {
     static constexpr int kMaxLen = 64;
@@ -56,7 +59,11 @@ struct PackArgs {
     uint8_t *seam_head;
     uint8_t *seam_tail;
     uint32_t *ticket;
+    uint32_t *tile_bits;               // [num_tiles] bits each tile emits (narrow path)
+    unsigned long long *group_prefix;  // [ceil(num_tiles / kGroupTiles)] bits before each group of tiles
 };
+constexpr int kGroupTiles = 256;
+static_assert(kGroupTiles == kPackThreads, "one thread per tile of a group sums the bits before a tile");
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane) {
 #pragma unroll
@@ -93,8 +100,266 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
     }
 }
 
-template <bool WIDE>
+// ------------------------------------------------------------------ narrow kernel (codes <= 32 bits)
+constexpr int kTableLanes = 16;
+constexpr int kTableBytes = 256 * kTableLanes * 8;                    // 32 KiB
+constexpr int kStageGuard = 4;                                        // zero words in front of the image
+constexpr int kStageWords = kStageGuard + kPackTileSyms + 8;          // worst case 32 bits per symbol
+constexpr int kPairs = kPackItems / 2;
+
+struct PackShared {
+    uint32_t warp_sum[kWarps];
+    unsigned long long group_part[kWarps];
+};
+
+// (acc << len) | code on a 64-bit accumulator, len 0..32, then hand a finished 32-bit word to
+// the staging image when there is one.
+__device__ __forceinline__ void push_bits(uint32_t &hi, uint32_t &lo, uint32_t &fill, uint32_t *&wp, uint32_t code,
+                                          uint32_t len) {
+    hi = __funnelshift_lc(lo, hi, len);
+    lo = __funnelshift_lc(0u, lo, len) | code;
+    fill += len;
+    if (fill >= 32u) {
+        fill -= 32u;
+        atomicOr(wp++, __funnelshift_r(lo, hi, fill));
+    }
+}
+
+// 16 input bytes of thread `tid` of `tile`, and which of them exist (edge tiles only).
+__device__ __forceinline__ uint4 load_symbols(const PackArgs &a, uint32_t tile, uint32_t tid, bool interior,
+                                              uint32_t *valid) {
+    const uint64_t v0 = (uint64_t)tile * kPackTileSyms + (uint64_t)tid * kPackItems;  // virtual byte index
+    *valid = 0xffffu;
+    if (interior) return ld_stream_v4(a.in_aligned + v0);
+    const long long lo = (long long)a.misalign - (long long)v0, hi = (long long)a.v_end - (long long)v0;
+    const int l = (int)max(lo, 0ll), h = (int)min(hi, 16ll);
+    if (h <= 0 || l >= 16) {
+        *valid = 0;
+        return make_uint4(0, 0, 0, 0);
+    }
+    *valid = (0xffffu >> (16 - h)) & (0xffffu << l);
+    return ld_partial_v4(a.in_aligned + v0, l, h);
+}
+__device__ __forceinline__ bool tile_is_interior(const PackArgs &a, uint32_t tile) {
+    return (uint64_t)tile * kPackTileSyms >= a.misalign && (uint64_t)(tile + 1) * kPackTileSyms <= a.v_end;
+}
+
+// ---- pass A: how many bits each tile emits.  Streaming: 16 B per thread, 16 byte-table lookups.
+__global__ void __launch_bounds__(kPackThreads) tile_bits_kernel(const PackArgs a) {
+    __shared__ uint32_t len_sh[256];
+    __shared__ uint32_t warp_sum[kWarps];
+    len_sh[threadIdx.x] = static_cast<const uint2 *>(a.tables)[threadIdx.x].y;
+    __syncthreads();
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        uint32_t valid;
+        const uint4 raw = load_symbols(a, tile, tid, tile_is_interior(a, tile), &valid);
+        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < kPackItems; ++i) {
+            const uint32_t len = len_sh[(rw[i >> 2] >> (8 * (i & 3))) & 0xffu];
+            bits += ((valid >> i) & 1u) ? len : 0u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+        if (lane == 0) warp_sum[warp] = bits;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int q = 0; q < kWarps; ++q) t += warp_sum[q];
+            a.tile_bits[tile] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- scan: bits before each group of kGroupTiles tiles (one block; a 4 GiB input has 4096 groups).
+__global__ void __launch_bounds__(1024) group_scan_kernel(const PackArgs a, uint32_t n_groups) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n_groups + 1023u) / 1024u;
+    const uint32_t g_lo = min(t * per, n_groups), g_hi = min(g_lo + per, n_groups);
+    unsigned long long sum = 0;
+    for (uint32_t g = g_lo; g < g_hi; ++g) {
+        unsigned long long gs = 0;
+        const uint32_t t_hi = min((g + 1) * (uint32_t)kGroupTiles, a.num_tiles);
+        for (uint32_t i = g * kGroupTiles; i < t_hi; ++i) gs += a.tile_bits[i];
+        a.group_prefix[g] = gs;  // group total for now
+        sum += gs;
+    }
+    part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long v = t >= (uint32_t)d ? part[t - d] : 0ull;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[t] - sum + a.bit_phase;
+    for (uint32_t g = g_lo; g < g_hi; ++g) {
+        const unsigned long long gs = a.group_prefix[g];
+        a.group_prefix[g] = run;
+        run += gs;
+    }
+}
+
+// ---- pass B: every tile is independent (its first bit is known), so there is no waiting between CTAs.
 __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *table = smem;                                              // [sym][lane & 15] x {code, len}
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + kTableBytes);
+    __shared__ PackShared sh;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const uint2 *src = static_cast<const uint2 *>(a.tables);
+        uint2 *dst = reinterpret_cast<uint2 *>(table);
+        for (int i = tid; i < 256 * kTableLanes; i += kPackThreads) dst[i] = src[i / kTableLanes];
+        for (int i = tid; i < kStageWords; i += kPackThreads) stage[i] = 0;
+    }
+    __syncthreads();
+    const uint8_t *table_lane = table + (lane & (kTableLanes - 1)) * 8;
+
+    for (uint32_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        // ---- (1) load + lookup
+        const bool interior = tile_is_interior(a, tile);  // uniform over the CTA
+        uint32_t valid;
+        const uint4 raw = load_symbols(a, tile, tid, interior, &valid);
+        // bits of the tiles of this group that come before this one (summed below)
+        const uint32_t group_first = tile / kGroupTiles * kGroupTiles;
+        unsigned long long before = (group_first + tid < tile) ? a.tile_bits[group_first + tid] : 0u;
+        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t pair_code[kPairs], pair_len[kPairs];
+        uint32_t my_bits = 0;
+        bool slow = !interior;
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) {
+            const uint32_t w = rw[j >> 1];
+            const int sa = 16 * (j & 1), sb = sa + 8;
+            // byte -> byte offset sym*128 into this lane's column of the table
+            const uint32_t oa = sa == 0 ? ((w << 7) & 0x7f80u) : ((w >> (sa - 7)) & 0x7f80u);
+            const uint32_t ob = (w >> (sb - 7)) & 0x7f80u;
+            uint2 ea = *reinterpret_cast<const uint2 *>(table_lane + oa);
+            uint2 eb = *reinterpret_cast<const uint2 *>(table_lane + ob);
+            if (!interior) {
+                if (!((valid >> (2 * j)) & 1u)) ea = make_uint2(0, 0);
+                if (!((valid >> (2 * j + 1)) & 1u)) eb = make_uint2(0, 0);
+            }
+            const uint32_t len = ea.y + eb.y;
+            slow |= len > 32u;
+            pair_len[j] = len;
+            pair_code[j] = __funnelshift_lc(0u, ea.x, eb.y) | eb.x;
+            my_bits += len;
+        }
+
+        // ---- (2) block scan of bit totals (and the sum of the earlier tiles of the group)
+        uint32_t incl = my_bits;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += up;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        if (lane == 31) sh.warp_sum[warp] = incl;
+        if (lane == 0) sh.group_part[warp] = before;
+        const bool tile_slow = __syncthreads_or(slow);  // B1
+        uint32_t warp_off = 0, tile_bits = 0;
+        unsigned long long bit_begin = a.group_prefix[tile / kGroupTiles];  // B_i: first bit of the tile in the output
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) {
+            const uint32_t s = sh.warp_sum[q];
+            if (q < (int)warp) warp_off += s;
+            tile_bits += s;
+            bit_begin += sh.group_part[q];
+        }
+        const uint32_t my_off = warp_off + incl - my_bits;  // first bit of this thread inside the tile
+        const unsigned long long bit_end = bit_begin + tile_bits;  // E_i
+        if (tid == 0) a.tile_state[tile] = bit_end;  // for the seam fix-up
+
+        // ---- (3) assemble at tile-relative positions: words hold stream bits MSB-first; all
+        // stores are ORs because the first and last word of a thread are shared with its neighbours
+        {
+            uint32_t fill = my_off & 31u;  // bits pending in the accumulator
+            uint32_t *wp = stage + kStageGuard + (my_off >> 5);
+            uint32_t hi = 0, lo = 0;
+            if (!tile_slow) {
+#pragma unroll
+                for (int j = 0; j < kPairs; ++j) push_bits(hi, lo, fill, wp, pair_code[j], pair_len[j]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w = rw[q], ok = valid >> (4 * q);
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k, w >>= 8, ok >>= 1) {
+                        const uint2 e = *reinterpret_cast<const uint2 *>(table_lane + (w & 0xffu) * (kTableLanes * 8));
+                        if (ok & 1u) push_bits(hi, lo, fill, wp, e.x, e.y);
+                    }
+                }
+            }
+            if (fill) atomicOr(wp, lo << (32u - fill));
+        }
+        __syncthreads();  // B2: image complete
+        uint8_t *first_byte = a.out + (bit_begin >> 3);              // byte holding bit B_i
+        const uint32_t align = (uint32_t)(reinterpret_cast<uintptr_t>(first_byte) & 15u);
+        uint8_t *gbase = first_byte - align;                         // frame byte k <-> gbase[k]
+        const uint32_t shift = align * 8 + (uint32_t)(bit_begin & 7);  // frame bit of tile bit 0 (< 128)
+        const uint32_t used_bits = shift + tile_bits;
+        const uint32_t n_chunks = (used_bits + 127u) >> 7;
+
+        // ---- (4) move the image to its frame position, swap to stream order, store whole owned
+        // bytes, park the shared ones in the seam arrays
+        {
+            const unsigned long long byte0 = bit_begin >> 3;
+            const unsigned long long full_lo = (bit_begin + 7) >> 3, full_hi = bit_end >> 3;  // owned bytes [lo,hi)
+            const uint32_t s_lo = (uint32_t)(full_lo - byte0) + align;                       // frame coordinates
+            const uint32_t s_hi = full_hi >= full_lo ? (uint32_t)(full_hi - byte0) + align : s_lo;
+            const bool has_head = (bit_begin & 7) != 0;
+            const bool has_tail = (bit_end & 7) != 0 && full_hi >= full_lo;
+            const uint32_t s_head = align;
+            const uint32_t s_tail = (uint32_t)(full_hi - byte0) + align;  // only meaningful when has_tail
+            if (tid == 0) {
+                if (!has_head) a.seam_head[tile] = 0;
+                if (!has_tail) a.seam_tail[tile] = 0;
+            }
+            // frame word f holds tile bits [32f - shift, 32f - shift + 32)
+            const uint32_t r = (32u - (shift & 31u)) & 31u;
+            const int back = (int)((shift + 31u) >> 5);  // image words the frame starts before the tile
+            for (uint32_t c = tid; c < n_chunks; c += kPackThreads) {
+                const uint32_t *src = stage + kStageGuard + (int)(4 * c) - back;
+                const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3], w4 = src[4];
+                uint4 v;
+                v.x = bswap32(__funnelshift_l(w1, w0, r));
+                v.y = bswap32(__funnelshift_l(w2, w1, r));
+                v.z = bswap32(__funnelshift_l(w3, w2, r));
+                v.w = bswap32(__funnelshift_l(w4, w3, r));
+                const uint32_t k0 = c * 16;
+                if (k0 >= s_lo && k0 + 16 <= s_hi) {
+                    st_stream_v4(gbase + k0, v);
+                } else {
+                    const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const uint8_t byte = (uint8_t)(vw[k >> 2] >> (8 * (k & 3)));
+                        const uint32_t kk = k0 + k;
+                        if (kk >= s_lo && kk < s_hi) gbase[kk] = byte;
+                        if (has_head && kk == s_head) a.seam_head[tile] = byte;
+                        if (has_tail && kk == s_tail) a.seam_tail[tile] = byte;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // B3: everyone has read the image
+        for (uint32_t i = tid; i < ((tile_bits + 31u) >> 5) + 1u; i += kPackThreads) stage[kStageGuard + i] = 0;
+        // the next tile's B1 separates this zeroing from the next assembly
+    }
+}
+
+// ------------------------------------------------------------------ wide kernel (codes of 33..64 bits)
+template <bool WIDE>
+__global__ void __launch_bounds__(kPackThreads) pack_wide_kernel(const PackArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem);
     uint8_t *table = smem + StageWords<WIDE>::value * 4;
@@ -315,15 +580,19 @@ PackGeometry pack_geometry(const void *d_in, size_t n) {
 }
 
 size_t pack_scratch_bytes(uint32_t num_tiles) {
-    // [ticket + pad : 16][tile_state : 8*T][seam_head : T][seam_tail : T]
-    return 16 + (size_t)num_tiles * 10 + 16;
+    // [ticket + pad : 16][tile_state : 8*T][group_prefix : 8*G][tile_bits : 4*T][seam_head : T][seam_tail : T]
+    const size_t groups = ((size_t)num_tiles + kGroupTiles - 1) / kGroupTiles;
+    return 16 + (size_t)num_tiles * 14 + groups * 8 + 16;
 }
 PackScratch pack_scratch_carve(void *base, uint32_t num_tiles) {
     PackScratch s;
+    const size_t groups = ((size_t)num_tiles + kGroupTiles - 1) / kGroupTiles;
     uint8_t *p = static_cast<uint8_t *>(base);
     s.ticket = reinterpret_cast<uint32_t *>(p);
     s.tile_state = reinterpret_cast<unsigned long long *>(p + 16);
-    s.seam_head = p + 16 + (size_t)num_tiles * 8;
+    s.group_prefix = s.tile_state + num_tiles;
+    s.tile_bits = reinterpret_cast<uint32_t *>(s.group_prefix + groups);
+    s.seam_head = reinterpret_cast<uint8_t *>(s.tile_bits + num_tiles);
     s.seam_tail = s.seam_head + num_tiles;
     return s;
 }
@@ -332,8 +601,7 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
                         cudaStream_t stream, int *launches) {
     if (g.num_tiles == 0) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(scratch_base, 0, scratch_bytes, stream);
-    if (err != cudaSuccess) return err;
+    cudaError_t err = cudaSuccess;
     PackArgs a;
     a.in_aligned = g.in_aligned;
     a.misalign = g.misalign;
@@ -346,28 +614,45 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
     a.seam_head = s.seam_head;
     a.seam_tail = s.seam_tail;
     a.ticket = s.ticket;
+    a.tile_bits = s.tile_bits;
+    a.group_prefix = s.group_prefix;
 
-    const int smem_narrow = StageWords<false>::value * 4 + PackCfg<false>::kTableBytes;
-    const int smem_wide = StageWords<true>::value * 4 + PackCfg<true>::kTableBytes;
-    err = wide ? cudaFuncSetAttribute(pack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wide)
-               : cudaFuncSetAttribute(pack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_narrow);
-    if (err != cudaSuccess) return err;
-    // persistent CTAs: as many as fit per SM (smem-limited), never more than there are tiles
-    const int smem = wide ? smem_wide : smem_narrow;
-    int per_sm = (227 * 1024) / (smem + 1024);
-    if (per_sm > 2048 / kPackThreads) per_sm = 2048 / kPackThreads;
-    if (per_sm < 1) per_sm = 1;
-    unsigned grid = (unsigned)num_sms * (unsigned)per_sm;
-    if (grid > g.num_tiles) grid = g.num_tiles;
-    if (wide)
-        pack_kernel<true><<<grid, kPackThreads, smem, stream>>>(a);
-    else
-        pack_kernel<false><<<grid, kPackThreads, smem, stream>>>(a);
+    if (wide) {
+        // look-back descriptors and the ticket start from zero
+        err = cudaMemsetAsync(scratch_base, 0, 16 + (size_t)g.num_tiles * 8, stream);
+        if (err != cudaSuccess) return err;
+        const int smem = StageWords<true>::value * 4 + PackCfg<true>::kTableBytes;
+        err = cudaFuncSetAttribute(pack_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return err;
+        int per_sm = (227 * 1024) / (smem + 1024);
+        if (per_sm > 2048 / kPackThreads) per_sm = 2048 / kPackThreads;
+        if (per_sm < 1) per_sm = 1;
+        unsigned grid = (unsigned)num_sms * (unsigned)per_sm;
+        if (grid > g.num_tiles) grid = g.num_tiles;
+        pack_wide_kernel<true><<<grid, kPackThreads, smem, stream>>>(a);
+        if (launches) *launches += 1;
+    } else {
+        (void)scratch_bytes;
+        const int smem = kTableBytes + kStageWords * 4;
+        err = cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return err;
+        const uint32_t groups = (g.num_tiles + kGroupTiles - 1) / kGroupTiles;
+        unsigned grid_a = (unsigned)num_sms * 8u;
+        if (grid_a > g.num_tiles) grid_a = g.num_tiles;
+        tile_bits_kernel<<<grid_a, kPackThreads, 0, stream>>>(a);
+        group_scan_kernel<<<1, 1024, 0, stream>>>(a, groups);
+        int per_sm = (227 * 1024) / (smem + 1024);
+        if (per_sm > 2048 / kPackThreads) per_sm = 2048 / kPackThreads;
+        unsigned grid = (unsigned)num_sms * (unsigned)per_sm;  // persistent CTAs: the table is loaded once per CTA
+        if (grid > g.num_tiles) grid = g.num_tiles;
+        pack_kernel<<<grid, kPackThreads, smem, stream>>>(a);
+        if (launches) *launches += 3;
+    }
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     seam_fixup_kernel<<<(g.num_tiles + 255) / 256, 256, 0, stream>>>(s.tile_state, s.seam_head, s.seam_tail,
                                                                     g.num_tiles, bit_phase, d_out);
-    if (launches) *launches += 2;
+    if (launches) *launches += 1;
     return cudaGetLastError();
 }
 

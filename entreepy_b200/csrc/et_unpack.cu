@@ -67,6 +67,11 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -171,11 +176,9 @@ __device__ __forceinline__ uint32_t flush_row(uint32_t c, OutRow &r) {
     for (uint32_t b = 0; b < nblk; ++b) {
         const uint32_t s = r.row_s + 32u * b;
         const uint4 v0 = lds_v4(s), v1 = lds_v4(s + 16);
-        if (r.head_skip) {
-            const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-                if ((uint32_t)k >= r.head_skip) r.gblock[k] = (uint8_t)(vw[k >> 2] >> (8 * (k & 3)));
+        if (r.head_skip) {  // first sector of the chunk: its leading bytes belong to the chunk before
+            (void)v0; (void)v1;
+            for (uint32_t j = r.head_skip; j < 32u; ++j) r.gblock[j] = (uint8_t)lds_u8(s + j);
             r.head_skip = 0;
         } else {
             *reinterpret_cast<uint4 *>(r.gblock) = v0;
@@ -380,7 +383,7 @@ __device__ __forceinline__ uint32_t count_chunk_fast(const DecArgs &a, const Chu
     return count_piece<true>(w, c, clut_s, a.wlut, a.nodes);
 }
 
-__global__ void __launch_bounds__(kChunkThreads) chunk_sync_kernel(const DecArgs a, int round) {
+__global__ void __launch_bounds__(kChunkThreads, 8) chunk_sync_kernel(const DecArgs a, int round) {
     __shared__ __align__(16) uint32_t clut_sh[kLutSize];
     const uint32_t c = blockIdx.x * kChunkThreads + threadIdx.x;
     uint32_t start = 0;
