@@ -59,11 +59,10 @@ struct PackArgs {
     uint8_t *seam_head;
     uint8_t *seam_tail;
     uint32_t *ticket;
-    uint32_t *tile_bits;               // [num_tiles] bits each tile emits (narrow path)
-    unsigned long long *group_prefix;  // [ceil(num_tiles / kGroupTiles)] bits before each group of tiles
+    uint32_t *tile_bits;               // [num_tiles] bits of the earlier tiles of the same group (narrow path)
+    unsigned long long *group_prefix;  // [n_groups] bits before each group of tiles
+    uint32_t group_tiles;              // tiles per group
 };
-constexpr int kGroupTiles = 256;
-static_assert(kGroupTiles == kPackThreads, "one thread per tile of a group sums the bits before a tile");
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane) {
 #pragma unroll
@@ -109,7 +108,6 @@ constexpr int kPairs = kPackItems / 2;
 
 struct PackShared {
     uint32_t warp_sum[kWarps];
-    unsigned long long group_part[kWarps];
 };
 
 // (acc << len) | code on a 64-bit accumulator, len 0..32, then hand a finished 32-bit word to
@@ -144,51 +142,55 @@ __device__ __forceinline__ bool tile_is_interior(const PackArgs &a, uint32_t til
     return (uint64_t)tile * kPackTileSyms >= a.misalign && (uint64_t)(tile + 1) * kPackTileSyms <= a.v_end;
 }
 
-// ---- pass A: how many bits each tile emits.  Streaming: 16 B per thread, 16 byte-table lookups.
+// ---- pass A: one CTA per group of tiles.  For every tile: the bits the earlier tiles of the
+// group emit; for the group: its total.  Streaming: 16 B per thread, 16 byte-table lookups.
 __global__ void __launch_bounds__(kPackThreads) tile_bits_kernel(const PackArgs a) {
     __shared__ uint32_t len_sh[256];
-    __shared__ uint32_t warp_sum[kWarps];
+    __shared__ uint32_t warp_sum[2][kWarps];
     len_sh[threadIdx.x] = static_cast<const uint2 *>(a.tables)[threadIdx.x].y;
     __syncthreads();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        uint32_t valid;
-        const uint4 raw = load_symbols(a, tile, tid, tile_is_interior(a, tile), &valid);
-        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+    const uint32_t t_lo = blockIdx.x * a.group_tiles, t_hi = min(t_lo + a.group_tiles, a.num_tiles);
+    uint32_t run = 0;  // bits of the group so far (same value in every thread)
+    for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
         uint32_t bits = 0;
+        if (tile_is_interior(a, tile)) {
+            const uint4 raw = ld_stream_v4(a.in_aligned + (uint64_t)tile * kPackTileSyms + (uint64_t)tid * kPackItems);
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-        for (int i = 0; i < kPackItems; ++i) {
-            const uint32_t len = len_sh[(rw[i >> 2] >> (8 * (i & 3))) & 0xffu];
-            bits += ((valid >> i) & 1u) ? len : 0u;
+            for (int q = 0; q < 4; ++q)
+                bits += len_sh[rw[q] & 0xffu] + len_sh[(rw[q] >> 8) & 0xffu] + len_sh[(rw[q] >> 16) & 0xffu] +
+                        len_sh[rw[q] >> 24];
+        } else {
+            uint32_t valid;
+            const uint4 raw = load_symbols(a, tile, tid, false, &valid);
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int i = 0; i < kPackItems; ++i) {
+                const uint32_t len = len_sh[(rw[i >> 2] >> (8 * (i & 3))) & 0xffu];
+                bits += ((valid >> i) & 1u) ? len : 0u;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
-        if (lane == 0) warp_sum[warp] = bits;
+        uint32_t *ws = warp_sum[(tile - t_lo) & 1];  // double-buffered: one barrier per tile
+        if (lane == 0) ws[warp] = bits;
         __syncthreads();
-        if (tid == 0) {
-            uint32_t t = 0;
+        if (tid == 0) a.tile_bits[tile] = run;
 #pragma unroll
-            for (int q = 0; q < kWarps; ++q) t += warp_sum[q];
-            a.tile_bits[tile] = t;
-        }
-        __syncthreads();
+        for (int q = 0; q < kWarps; ++q) run += ws[q];
     }
+    if (tid == 0) a.group_prefix[blockIdx.x] = run;  // group total; group_scan_kernel turns it into a prefix
 }
 
-// ---- scan: bits before each group of kGroupTiles tiles (one block; a 4 GiB input has 4096 groups).
+// ---- scan: bits before each group (one block; groups are sized so that there are at most a few thousand).
 __global__ void __launch_bounds__(1024) group_scan_kernel(const PackArgs a, uint32_t n_groups) {
     __shared__ unsigned long long part[1024];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (n_groups + 1023u) / 1024u;
     const uint32_t g_lo = min(t * per, n_groups), g_hi = min(g_lo + per, n_groups);
     unsigned long long sum = 0;
-    for (uint32_t g = g_lo; g < g_hi; ++g) {
-        unsigned long long gs = 0;
-        const uint32_t t_hi = min((g + 1) * (uint32_t)kGroupTiles, a.num_tiles);
-        for (uint32_t i = g * kGroupTiles; i < t_hi; ++i) gs += a.tile_bits[i];
-        a.group_prefix[g] = gs;  // group total for now
-        sum += gs;
-    }
+    for (uint32_t g = g_lo; g < g_hi; ++g) sum += a.group_prefix[g];
     part[t] = sum;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
     uint8_t *table = smem;                                              // [sym][lane & 15] x {code, len}
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem + kTableBytes);
     __shared__ PackShared sh;
+    __shared__ __align__(16) uint8_t edge_sh[2][16];  // first / last block of a tile, for bytewise stores
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
@@ -227,9 +230,6 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
         const bool interior = tile_is_interior(a, tile);  // uniform over the CTA
         uint32_t valid;
         const uint4 raw = load_symbols(a, tile, tid, interior, &valid);
-        // bits of the tiles of this group that come before this one (summed below)
-        const uint32_t group_first = tile / kGroupTiles * kGroupTiles;
-        unsigned long long before = (group_first + tid < tile) ? a.tile_bits[group_first + tid] : 0u;
         const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
         uint32_t pair_code[kPairs], pair_len[kPairs];
         uint32_t my_bits = 0;
@@ -261,19 +261,16 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
             const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= (uint32_t)d) incl += up;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
         if (lane == 31) sh.warp_sum[warp] = incl;
-        if (lane == 0) sh.group_part[warp] = before;
+        // B_i: first bit of the tile in the output
+        const unsigned long long bit_begin = a.group_prefix[tile / a.group_tiles] + a.tile_bits[tile];
         const bool tile_slow = __syncthreads_or(slow);  // B1
         uint32_t warp_off = 0, tile_bits = 0;
-        unsigned long long bit_begin = a.group_prefix[tile / kGroupTiles];  // B_i: first bit of the tile in the output
 #pragma unroll
         for (int q = 0; q < kWarps; ++q) {
             const uint32_t s = sh.warp_sum[q];
             if (q < (int)warp) warp_off += s;
             tile_bits += s;
-            bit_begin += sh.group_part[q];
         }
         const uint32_t my_off = warp_off + incl - my_bits;  // first bit of this thread inside the tile
         const unsigned long long bit_end = bit_begin + tile_bits;  // E_i
@@ -339,15 +336,14 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
                 if (k0 >= s_lo && k0 + 16 <= s_hi) {
                     st_stream_v4(gbase + k0, v);
                 } else {
-                    const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const uint8_t byte = (uint8_t)(vw[k >> 2] >> (8 * (k & 3)));
-                        const uint32_t kk = k0 + k;
-                        if (kk >= s_lo && kk < s_hi) gbase[kk] = byte;
-                        if (has_head && kk == s_head) a.seam_head[tile] = byte;
-                        if (has_tail && kk == s_tail) a.seam_tail[tile] = byte;
-                    }
+                    // a block at the ragged start or end of the tile: through a small per-thread buffer
+                    uint4 *tmp = reinterpret_cast<uint4 *>(edge_sh[c == 0 ? 0 : 1]);
+                    *tmp = v;
+                    const uint8_t *tb = reinterpret_cast<const uint8_t *>(tmp);
+                    const uint32_t lo_k = max(k0, s_lo), hi_k = min(k0 + 16u, s_hi);
+                    for (uint32_t kk = lo_k; kk < hi_k; ++kk) gbase[kk] = tb[kk - k0];
+                    if (has_head && s_head >= k0 && s_head < k0 + 16u) a.seam_head[tile] = tb[s_head - k0];
+                    if (has_tail && s_tail >= k0 && s_tail < k0 + 16u) a.seam_tail[tile] = tb[s_tail - k0];
                 }
             }
         }
@@ -366,6 +362,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_wide_kernel(const PackArgs 
     __shared__ uint32_t warp_sum[kWarps];
     __shared__ unsigned long long tile_base_sh;
     __shared__ uint32_t tile_sh;
+    __shared__ __align__(16) uint8_t edge_sh[2][16];  // first / last block of a tile, for bytewise stores
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -528,15 +525,14 @@ __global__ void __launch_bounds__(kPackThreads) pack_wide_kernel(const PackArgs 
                 if (k0 >= s_lo && k0 + 16 <= s_hi) {
                     st_stream_v4(gbase + k0, v);
                 } else {
-                    const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const uint8_t byte = (uint8_t)(vw[k >> 2] >> (8 * (k & 3)));
-                        const uint32_t kk = k0 + k;
-                        if (kk >= s_lo && kk < s_hi) gbase[kk] = byte;
-                        if (has_head && kk == s_head) a.seam_head[tile] = byte;
-                        if (has_tail && kk == s_tail) a.seam_tail[tile] = byte;
-                    }
+                    // a block at the ragged start or end of the tile: through a small per-thread buffer
+                    uint4 *tmp = reinterpret_cast<uint4 *>(edge_sh[c == 0 ? 0 : 1]);
+                    *tmp = v;
+                    const uint8_t *tb = reinterpret_cast<const uint8_t *>(tmp);
+                    const uint32_t lo_k = max(k0, s_lo), hi_k = min(k0 + 16u, s_hi);
+                    for (uint32_t kk = lo_k; kk < hi_k; ++kk) gbase[kk] = tb[kk - k0];
+                    if (has_head && s_head >= k0 && s_head < k0 + 16u) a.seam_head[tile] = tb[s_head - k0];
+                    if (has_tail && s_tail >= k0 && s_tail < k0 + 16u) a.seam_tail[tile] = tb[s_tail - k0];
                 }
             }
         }
@@ -579,14 +575,22 @@ PackGeometry pack_geometry(const void *d_in, size_t n) {
     return g;
 }
 
+// Tiles per group: groups are the CTAs of pass A and the entries of the one-block scan, so
+// there should be a few per SM but no more than a few thousand.
+static uint32_t pack_group_tiles(uint32_t num_tiles) {
+    uint32_t gt = 8;
+    while (gt < 256 && num_tiles / gt > 2048) gt <<= 1;
+    while (num_tiles / gt > 8192) gt <<= 1;
+    return gt;
+}
 size_t pack_scratch_bytes(uint32_t num_tiles) {
     // [ticket + pad : 16][tile_state : 8*T][group_prefix : 8*G][tile_bits : 4*T][seam_head : T][seam_tail : T]
-    const size_t groups = ((size_t)num_tiles + kGroupTiles - 1) / kGroupTiles;
+    const size_t groups = ((size_t)num_tiles + 7) / 8;
     return 16 + (size_t)num_tiles * 14 + groups * 8 + 16;
 }
 PackScratch pack_scratch_carve(void *base, uint32_t num_tiles) {
     PackScratch s;
-    const size_t groups = ((size_t)num_tiles + kGroupTiles - 1) / kGroupTiles;
+    const size_t groups = ((size_t)num_tiles + 7) / 8;
     uint8_t *p = static_cast<uint8_t *>(base);
     s.ticket = reinterpret_cast<uint32_t *>(p);
     s.tile_state = reinterpret_cast<unsigned long long *>(p + 16);
@@ -616,6 +620,7 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
     a.ticket = s.ticket;
     a.tile_bits = s.tile_bits;
     a.group_prefix = s.group_prefix;
+    a.group_tiles = 1;
 
     if (wide) {
         // look-back descriptors and the ticket start from zero
@@ -636,10 +641,9 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         const int smem = kTableBytes + kStageWords * 4;
         err = cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err != cudaSuccess) return err;
-        const uint32_t groups = (g.num_tiles + kGroupTiles - 1) / kGroupTiles;
-        unsigned grid_a = (unsigned)num_sms * 8u;
-        if (grid_a > g.num_tiles) grid_a = g.num_tiles;
-        tile_bits_kernel<<<grid_a, kPackThreads, 0, stream>>>(a);
+        a.group_tiles = pack_group_tiles(g.num_tiles);
+        const uint32_t groups = (g.num_tiles + a.group_tiles - 1) / a.group_tiles;
+        tile_bits_kernel<<<groups, kPackThreads, 0, stream>>>(a);
         group_scan_kernel<<<1, 1024, 0, stream>>>(a, groups);
         int per_sm = (227 * 1024) / (smem + 1024);
         if (per_sm > 2048 / kPackThreads) per_sm = 2048 / kPackThreads;

@@ -6,7 +6,7 @@ from collections import Counter
 
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]
-data = [r for r in rows[2:] if len(r) == len(hdr)]
+data = [r for r in rows[2:] if len(r) == len(hdr) and r[hdr.index('Instructions Executed')].isdigit()]
 ia, isrc, ist = hdr.index('Instructions Executed'), hdr.index('Source'), hdr.index('# Samples')
 iw, iwi = hdr.index('L1 Wavefronts Shared'), hdr.index('L1 Wavefronts Shared Ideal')
 tot = sum(int(r[ia]) for r in data)
