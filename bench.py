@@ -196,11 +196,110 @@ def run_reference(args, rank):
 
 
 # ---------------------------------------------------------------------------------- GPU arm
+class OneGpu:
+    """N=1: the drop-in entry points et_encode_dev / et_decode_dev on one whole stream."""
+
+    def __init__(self, codec, n, stream):
+        import torch
+
+        from entreepy_b200 import _abi
+
+        self.codec, self.n, self.stream = codec, n, stream
+        self.enc = torch.empty(n + 16384, dtype=torch.uint8, device="cuda")
+        self.dec = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+        self.flags = _abi.FLAG_WRITE_OUTPUT | _abi.FLAG_TIMING
+        self.size = 0
+
+    def encode(self, inp):
+        self.size = self.codec.encode_dev(inp.data_ptr(), self.n, self.enc.data_ptr(), self.enc.numel(), self.flags, self.stream)
+        return self.size - self.header_bytes()
+
+    def header_bytes(self):
+        if not hasattr(self, "_hb"):
+            import entreepy_b200 as et
+
+            self._hb = 4 + int(et.parse_header(self.enc[4:4100].cpu().numpy()).body_offset)
+        return self._hb
+
+    def prepare_decode(self):
+        pass
+
+    def decode(self):
+        got = self.codec.decode_dev(self.enc.data_ptr() + 4, self.size - 4, self.dec.data_ptr(), self.n, self.flags, self.stream)
+        return got, 0
+
+    def e2e_buffers(self):
+        c = self.codec
+        return c.pinned(self.n), c.pinned(self.n + 16384), c.pinned(self.n)
+
+    def e2e_step(self, h_in, h_enc, h_dec):
+        import entreepy_b200 as et
+
+        size = self.codec.encode_into(h_in, h_enc, et.EncodeFlags(write_output=True))
+        got = self.codec.decode_into(h_enc[4:size], h_dec, et.DecodeFlags(write_output=True))
+        return got, int(self.n + size - 4), int(size + self.n)
+
+
+class ManyGpus:
+    """N>1: one stream sharded over the ranks (entreepy_b200.sharded on the shard entry points)."""
+
+    def __init__(self, codec, plan, dist, stream):
+        import torch
+
+        from entreepy_b200 import sharded
+
+        self.codec, self.plan, self.dist = codec, plan, dist
+        self.coder = sharded.ShardedCodec(sharded.GpuBackend(codec, stream), plan, sharded.Comm(dist, torch.device("cuda")))
+        self.body = torch.empty(plan.n_local + 16384, dtype=torch.uint8, device="cuda")
+        self.res = self.range = self.dec = None
+
+    def encode(self, inp):
+        self.res = self.coder.encode(inp, self.body)
+        return self.res.own_hi - self.res.own_lo
+
+    def prepare_decode(self):
+        """What a file reader would do: give every rank its equal share of the body (untimed setup)."""
+        import torch
+
+        self.range = self.coder.scatter_body(self.res, self.body).clone()
+        cuts, ranges = self.coder.decode_ranges(self.res.body_bytes)
+        self.own_body = cuts[self.plan.rank + 1] - cuts[self.plan.rank]
+        # text of an equal share of the body: about n_total / world symbols; leave generous room
+        self.dec = torch.empty(int(self.plan.n_total / self.plan.world * 1.25) + (1 << 20), dtype=torch.uint8, device="cuda")
+
+    def decode(self):
+        d = self.coder.decode(self.res.header[4:], self.res.body_bytes, self.range, self.dec)
+        self.rounds = d.rounds
+        return d.n_local, d.offset
+
+    def e2e_buffers(self):
+        import torch
+
+        return (torch.empty(self.plan.n_local, dtype=torch.uint8).pin_memory(),
+                torch.empty(self.body.numel(), dtype=torch.uint8).pin_memory(),
+                (torch.empty(self.range.numel(), dtype=torch.uint8).pin_memory(),
+                 torch.empty(self.dec.numel(), dtype=torch.uint8).pin_memory()))
+
+    def e2e_step(self, h_in, h_body, h_pair, inp):
+        import torch
+
+        h_range, h_text = h_pair
+        inp[: self.plan.n_local].copy_(h_in, non_blocking=True)
+        res = self.coder.encode(inp, self.body)
+        nb = res.own_hi - res.own_lo
+        h_body[:nb].copy_(self.body[res.own_lo - res.first_byte : res.own_hi - res.first_byte], non_blocking=True)
+        self.range.copy_(h_range, non_blocking=True)
+        d = self.coder.decode(res.header[4:], res.body_bytes, self.range, self.dec)
+        h_text[: d.n_local].copy_(self.dec[: d.n_local], non_blocking=True)
+        torch.cuda.synchronize()
+        return d.n_local, int(self.plan.n_local + self.range.numel()), int(nb + d.n_local)
+
+
 def run_ours(args, rank, world):
     import torch
 
     import entreepy_b200 as et
-    from entreepy_b200 import _abi, sharded, synth
+    from entreepy_b200 import sharded, synth
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -216,6 +315,7 @@ def run_ours(args, rank, world):
     plan = sharded.ShardPlan(n_total, world, rank)
     n = plan.n_local
     stream = torch.cuda.current_stream().cuda_stream
+    thr = thresholds(kind) if kind != "file" else None
 
     # ---- synthetic input, generated on the device (same bytes as entreepy_b200/synth.py on the CPU)
     inp = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
@@ -223,36 +323,45 @@ def run_ours(args, rank, world):
         data = host_sample(kind, n_total)[plan.lo:plan.hi]
         inp[:n].copy_(torch.from_numpy(data.copy()))
     else:
-        codec.synth_dev(inp.data_ptr(), n, synth.SEED, plan.lo, thresholds(kind))
-    enc = torch.empty(n + 16384, dtype=torch.uint8, device="cuda")
-    dec = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
-    enc_flags = _abi.FLAG_WRITE_OUTPUT | _abi.FLAG_TIMING
-    dec_flags = _abi.FLAG_WRITE_OUTPUT | _abi.FLAG_TIMING
-    coder = sharded.ShardedCodec(codec, plan, dist)
-
-    def step(stats=None):
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
-        res = coder.encode(inp.data_ptr(), enc.data_ptr(), enc.numel(), enc_flags, stream)
-        ms_enc = codec.last_stage_ms()
-        e1.record()
-        got = coder.decode(res, enc.data_ptr(), dec.data_ptr(), n, dec_flags, stream)
-        ms_dec = codec.last_stage_ms() + [codec.last_decode_rounds]
-        e2.record()
-        if stats is not None:
-            stats.append((e0, e1, e2, ms_enc, ms_dec))
-        return res, got
+        codec.synth_dev(inp.data_ptr(), n, synth.SEED, plan.lo, thr)
+    arm = OneGpu(codec, n, stream) if world == 1 else ManyGpus(codec, plan, dist, stream)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def step(stats=None):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        c_local = arm.encode(inp)
+        ms_enc = codec.last_stage_ms()
+        e1.record()
+        got, offset = arm.decode()
+        ms_dec = codec.last_stage_ms() + [codec.last_decode_rounds]
+        e2.record()
+        if stats is not None:
+            stats.append((e0, e1, e2, ms_enc, ms_dec))
+        return c_local, got, offset
+
+    c_local = arm.encode(inp)
+    arm.prepare_decode()
     for _ in range(max(args.warmup, 3)):
-        res, got = step()
+        c_local, got, offset = step()
     barrier()
-    assert got == n, f"decode produced {got} of {n} bytes"
-    verified = bool(torch.equal(dec[:n], inp[:n]))  # round trip == original (north_star)
+    # round trip == original (north_star): the text this rank decoded is text[offset : offset + got]
+    if world == 1:
+        verified = got == n and bool(torch.equal(arm.dec[:n], inp[:n]))
+    else:
+        want = torch.empty(got + 16, dtype=torch.uint8, device="cuda")
+        if kind == "file":
+            want[:got].copy_(torch.from_numpy(host_sample(kind, n_total)[offset:offset + got].copy()))
+        else:
+            codec.synth_dev(want.data_ptr(), got, synth.SEED, offset, thr)
+        ok = torch.tensor([int(torch.equal(arm.dec[:got], want[:got])), got], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ok)
+        verified = int(ok[0].item()) == world and int(ok[1].item()) == n_total
+        del want
     if not verified:
         raise SystemExit("bench.py: decode(encode(x)) != x — refusing to report a throughput")
 
@@ -269,18 +378,21 @@ def run_ours(args, rank, world):
         barrier()
     total_ms = t_begin.elapsed_time(t_end)
     launches = codec.kernel_launches - launches0
+    enc_ms = statistics.mean(s[0].elapsed_time(s[1]) for s in stats)
+    dec_ms = statistics.mean(s[1].elapsed_time(s[2]) for s in stats)
     if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        total_ms, enc_ms, dec_ms = (float(v) for v in t.tolist())
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     ms_step = total_ms / args.steps
-    enc_ms = [s[0].elapsed_time(s[1]) for s in stats]
-    dec_ms = [s[1].elapsed_time(s[2]) for s in stats]
     hist_ms = statistics.mean(s[3][0] for s in stats)
     host_ms = statistics.mean(s[3][1] for s in stats)
     pack_ms = statistics.mean(s[3][2] for s in stats)
     unpack_ms = statistics.mean(s[4][2] for s in stats)
-    c_local = res.local_bytes  # compressed bytes this rank wrote
+    c_dec = c_local if world == 1 else arm.own_body  # compressed bytes this rank decodes
     peak, peak_src = peaks()
 
     def roof(kernel, alg_bytes, ms):
@@ -288,14 +400,16 @@ def run_ours(args, rank, world):
         return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic_for(kernel), "algorithmic_bytes": alg_bytes, "ms": ms, "peak_source": peak_src}
 
-    roofs = [roof("histogram_kernel", n, hist_ms), roof("pack_kernel", n + c_local, pack_ms),
-             roof("unpack_kernel", c_local + n, unpack_ms)]
+    roofs = [roof("pack (tile_bits_kernel + pack_kernel)", n + c_local, pack_ms),
+             roof("unpack (chunk_sync_kernel + chunk_write_kernel)", c_dec + got, unpack_ms)]
+    if world == 1:
+        roofs.insert(0, roof("histogram_kernel", n, hist_ms))
     dominant = max(roofs, key=lambda r: r["ms"])
 
-    # ---- end to end through the host-buffer entry points (pinned memory, copies inside the timed region)
+    # ---- end to end with pinned HOST buffers (copies inside the timed region)
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, codec, coder, inp, n, res, dist, barrier)
+        e2e = run_e2e(args, arm, inp, n, n_total, world, dist, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -315,16 +429,14 @@ def run_ours(args, rank, world):
             "config": {"workload": args.workload, "bytes": n_total, "bytes_per_rank": n, "compressed_bytes_rank0": c_local,
                        "sharding": f"{world} contiguous byte ranges of one .et stream" if world > 1 else "none",
                        "l2": "inputs larger than L2 (126 MB), no explicit flush"},
-            "encode_gbs": n_total / 1e9 / (statistics.mean(enc_ms) / 1e3),
-            "decode_gbs": n_total / 1e9 / (statistics.mean(dec_ms) / 1e3),
-            "encode_ms": statistics.mean(enc_ms), "decode_ms": statistics.mean(dec_ms),
+            "encode_gbs": n_total / 1e9 / (enc_ms / 1e3), "decode_gbs": n_total / 1e9 / (dec_ms / 1e3),
+            "encode_ms": enc_ms, "decode_ms": dec_ms,
             "stage_ms": {"histogram": hist_ms, "host_codebook": host_ms, "pack": pack_ms, "unpack": unpack_ms},
             "roofline": dominant, "rooflines": roofs,
-            "encode_frac_of_hbm": (2 * n + c_local) / 1e9 / (statistics.mean(enc_ms) / 1e3) / peak,
-            "decode_frac_of_hbm": (n + c_local) / 1e9 / (statistics.mean(dec_ms) / 1e3) / peak,
+            "encode_frac_of_hbm": (2 * n + c_local) / 1e9 / (enc_ms / 1e3) / peak,
+            "decode_frac_of_hbm": (got + c_dec) / 1e9 / (dec_ms / 1e3) / peak,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "verified_round_trip": verified,
-            "decode_check_rounds": stats[-1][4][4],
-            "clocks": clocks.summary(),
+            "decode_check_rounds": stats[-1][4][4], "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -333,40 +445,44 @@ def run_ours(args, rank, world):
     return 0
 
 
-def run_e2e(args, codec, coder, inp, n, res, dist, barrier):
-    """Same step through et_encode / et_decode with pinned host buffers."""
+def run_e2e(args, arm, inp, n, n_total, world, dist, barrier):
+    """The same step with pinned HOST buffers: N=1 through et_encode / et_decode (the reference-facing
+    calls); N>1 pinned host -> device copy, the sharded device path, device -> pinned host copy."""
     import torch
 
-    import entreepy_b200 as et
-
-    h_in = codec.pinned(n)
-    h_enc = codec.pinned(n + 16384)
-    h_dec = codec.pinned(n)
-    torch.from_numpy(h_in)[:] = inp[:n].cpu()
-    ef = et.EncodeFlags(write_output=True)
-    df = et.DecodeFlags(write_output=True)
+    h_in, h_enc, h_dec = arm.e2e_buffers()
     steps = max(1, min(args.steps, 3))
-    size = 0
-    times = []
+    if world == 1:
+        torch.from_numpy(h_in)[:] = inp[:n].cpu()
+    else:
+        h_in.copy_(inp[:n])
+        h_dec[0].copy_(arm.range)
+    times, h2d, d2h, got = [], 0, 0, 0
     for i in range(1 + steps):
         barrier()
         t0 = time.perf_counter()
-        size, info = coder.encode_host(h_in, h_enc, ef)
-        got = coder.decode_host(info, h_enc, h_dec, df)
+        if world == 1:
+            got, h2d, d2h = arm.e2e_step(h_in, h_enc, h_dec)
+        else:
+            got, h2d, d2h = arm.e2e_step(h_in, h_enc, h_dec, inp)
         barrier()
         if i >= 1:
             times.append(time.perf_counter() - t0)
-    assert got == n and np.array_equal(h_dec[: 1 << 20], h_in[: 1 << 20])
+    if world == 1:
+        assert got == n and np.array_equal(h_dec[: 1 << 20], h_in[: 1 << 20])
     sec = statistics.mean(times)
     if dist is not None:
         t = torch.tensor([sec], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
-    n_total = coder.plan.n_total
-    # per step: encode uploads n and reads back `size`; decode uploads `size` (minus magic) and reads back n
-    return {"value": n_total / 1e9 / sec, "unit": "GB/s", "h2d_bytes_per_step": int(n + size - 4),
-            "d2h_bytes_per_step": int(size + n), "steps": steps, "ms_per_step": sec * 1e3,
-            "path": "et_encode + et_decode (C ABI, pinned host buffers), wall clock around the blocking calls"}
+        b = torch.tensor([h2d, d2h], dtype=torch.int64, device="cuda")
+        dist.all_reduce(b)
+        h2d, d2h = (int(v) for v in b.tolist())
+    return {"value": n_total / 1e9 / sec, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "ms_per_step": sec * 1e3,
+            "path": ("et_encode + et_decode (C ABI, pinned host buffers)" if world == 1 else
+                     "pinned host -> device, sharded encode + decode (shard entry points of the C ABI), device -> pinned host")
+                    + ", wall clock around the blocking calls"}
 
 
 def main():

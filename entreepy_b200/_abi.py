@@ -90,10 +90,10 @@ def load():
         "et_decode": (i, [vp, vp, sz, vp, sz, szp, u32]),
         "et_encode_dev": (i, [vp, vp, sz, vp, sz, szp, u32, vp]),
         "et_decode_dev": (i, [vp, vp, sz, vp, sz, szp, u32, vp]),
-        "et_pack_shard_dev": (i, [vp, vp, sz, ctypes.POINTER(Codebook), u32, vp, sz, szp, ctypes.POINTER(u64), vp]),
+        "et_pack_shard_dev": (i, [vp, vp, sz, ctypes.POINTER(Codebook), u32, u64, vp, sz, szp, vp]),
         "et_shard_bits": (u64, [vp, ctypes.POINTER(Codebook)]),
-        "et_unpack_shard_dev": (i, [vp, vp, sz, ctypes.POINTER(Dictionary), u64, u64, u64, vp, sz,
-                                    ctypes.POINTER(u64), ctypes.POINTER(u64), vp]),
+        "et_unpack_shard_dev": (i, [vp, vp, sz, sz, sz, ctypes.POINTER(Dictionary), ctypes.c_int64, vp, sz,
+                                    ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(u64), vp]),
         "et_synth_dev": (i, [vp, vp, sz, u64, u64, vp, vp]),
     }
     for name, (res, args) in sig.items():

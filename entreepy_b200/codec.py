@@ -214,12 +214,24 @@ class Codec:
         self._check(self._lib.et_decode_dev(self._ctx, d_in_after_magic, n, d_out, cap, ctypes.byref(got), flags, stream))
         return got.value
 
-    def pack_shard_dev(self, d_in, n, cb, bit_phase, d_out, cap, stream=None):
-        """-> (bytes touched, bits) for one shard packed at bit `bit_phase` of d_out[0]."""
-        nbytes, bits = ctypes.c_size_t(0), ctypes.c_uint64(0)
-        self._check(self._lib.et_pack_shard_dev(self._ctx, d_in, n, ctypes.byref(cb), bit_phase, d_out, cap,
-                                                ctypes.byref(nbytes), ctypes.byref(bits), stream))
-        return nbytes.value, bits.value
+    def shard_bits(self, counts, cb):
+        c = np.ascontiguousarray(counts, dtype=np.uint64)
+        return int(self._lib.et_shard_bits(c.ctypes.data, ctypes.byref(cb)))
+
+    def pack_shard_dev(self, d_in, n, cb, bit_phase, shard_bits, d_out, cap, stream=None):
+        """-> bytes touched by one shard packed at bit `bit_phase` of d_out[0]."""
+        nbytes = ctypes.c_size_t(0)
+        self._check(self._lib.et_pack_shard_dev(self._ctx, d_in, n, ctypes.byref(cb), bit_phase, shard_bits, d_out, cap,
+                                                ctypes.byref(nbytes), stream))
+        return nbytes.value
+
+    def unpack_shard_dev(self, d_range, range_bytes, own_begin, own_end, dictionary, head_bit, d_out, cap, stream=None):
+        """-> (symbols, entry_bit, exit_bit) of one shard of the body (see et_unpack_shard_dev)."""
+        n, ent, ext = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        self._check(self._lib.et_unpack_shard_dev(self._ctx, d_range, range_bytes, own_begin, own_end, ctypes.byref(dictionary),
+                                                  head_bit, d_out, cap, ctypes.byref(n), ctypes.byref(ent), ctypes.byref(ext),
+                                                  stream))
+        return n.value, ent.value, ext.value
 
     def synth_dev(self, d_out, n, seed, first_index, thresholds, stream=None):
         t = np.ascontiguousarray(thresholds, dtype=np.uint32)

@@ -428,24 +428,24 @@ extern "C" int et_encode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
 }
 
 extern "C" int et_pack_shard_dev(et_ctx *ctx, const void *d_in, size_t n, const et_codebook *cb, uint32_t bit_phase,
-                                 void *d_out, size_t cap, size_t *out_bytes, uint64_t *bits, void *stream) {
+                                 uint64_t shard_bits, void *d_out, size_t cap, size_t *out_bytes, void *stream) {
     if (!ctx || !cb || !d_out || bit_phase > 7 || (!d_in && n)) return ET_ERR_INVALID_ARG;
     ET_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    // the shard's bit count comes from its own histogram under the shared codebook
-    uint64_t counts[256];
-    int rc = histogram_dev(ctx, d_in, n, counts, s);
-    if (rc != ET_OK) return rc;
-    const uint64_t nbits = et_shard_bits(counts, cb);
-    const size_t bytes = (size_t)((bit_phase + nbits + 7) >> 3);
+    const size_t bytes = (size_t)((bit_phase + shard_bits + 7) >> 3);
     if (bytes > cap) return fail(ctx, ET_ERR_NO_SPACE, "shard needs %zu bytes, capacity %zu", bytes, cap);
+    StageTimer tm{ctx, s, true};
+    tm.mark(0);
+    tm.mark(1);
+    tm.mark(2);
     if (n) {
-        rc = pack_dev(ctx, d_in, n, *cb, bit_phase, static_cast<uint8_t *>(d_out), s);
+        const int rc = pack_dev(ctx, d_in, n, *cb, bit_phase, static_cast<uint8_t *>(d_out), s);
         if (rc != ET_OK) return rc;
-        ET_CUDA(ctx, cudaStreamSynchronize(s));
     }
+    tm.mark(3);
+    ET_CUDA(ctx, cudaStreamSynchronize(s));
+    tm.finish(4);
     if (out_bytes) *out_bytes = bytes;
-    if (bits) *bits = nbits;
     return ET_OK;
 }
 
@@ -453,8 +453,8 @@ extern "C" int et_pack_shard_dev(et_ctx *ctx, const void *d_in, size_t n, const 
 namespace {
 
 // Decode a device-resident body.  *n_symbols = symbols the stream holds, capped at max_symbols.
-int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_dictionary &dict, uint8_t *d_out,
-               uint64_t max_symbols, uint64_t *n_symbols, cudaStream_t s, StageTimer *tm = nullptr) {
+int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, uint8_t *d_out, uint64_t max_symbols,
+               uint64_t *n_symbols, cudaStream_t s, StageTimer *tm = nullptr, uint32_t *entry_exit = nullptr) {
     UnpackTables *t = new (std::nothrow) UnpackTables;
     if (!t) return ET_ERR_OUT_OF_MEMORY;
     int rc = make_unpack_tables(dict, t);
@@ -470,7 +470,6 @@ int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_d
     ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffLut, ctx->h_small + kOffLut, tbl_bytes, cudaMemcpyHostToDevice, s));
     if (tm) tm->mark(2);
 
-    const UnpackGeometry g = unpack_geometry(d_body, body_bytes);
     const uint32_t chunk_bytes = unpack_chunk_bytes(g, ctx->num_sms);
     rc = ensure_scratch(ctx, unpack_scratch_bytes(g, chunk_bytes));
     if (rc != ET_OK) return rc;
@@ -483,13 +482,14 @@ int unpack_dev(et_ctx *ctx, const uint8_t *d_body, size_t body_bytes, const et_d
                                reinterpret_cast<uint32_t *>(ctx->h_small + kOffFlags + 32), s, &launches, &rounds));
     ctx->launches += (uint64_t)launches;
     ctx->last_decode_rounds = rounds;
-    // header of the scratch block: pad(4) | error flags(4) | symbols found(8)
-    ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffFlags, ctx->d_scratch, 16, cudaMemcpyDeviceToHost, s));
+    // header of the scratch block: pad(4) | error flags(4) | symbols found(8) | changed(4) | pad(4) | entry, exit (4+4)
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffFlags, ctx->d_scratch, 32, cudaMemcpyDeviceToHost, s));
     ET_CUDA(ctx, cudaStreamSynchronize(s));
     uint32_t flags = 0;
     unsigned long long total = 0;
     std::memcpy(&flags, ctx->h_small + kOffFlags + 4, 4);
     std::memcpy(&total, ctx->h_small + kOffFlags + 8, 8);
+    if (entry_exit) std::memcpy(entry_exit, ctx->h_small + kOffFlags + 24, 8);
     if (flags & kErrInvalidCode) return fail(ctx, ET_ERR_CORRUPT, "body contains a bit pattern that is not a code");
     *n_symbols = std::min<uint64_t>(total, max_symbols);
     return ET_OK;
@@ -520,7 +520,7 @@ extern "C" int et_decode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_ou
     if (!d_out && cap) return ET_ERR_INVALID_ARG;
     uint64_t produced = 0;
     const uint64_t want = std::min<uint64_t>(dict.body_len, cap);
-    rc = unpack_dev(ctx, static_cast<const uint8_t *>(d_in) + dict.body_offset, n - dict.body_offset, dict,
+    rc = unpack_dev(ctx, unpack_geometry(static_cast<const uint8_t *>(d_in) + dict.body_offset, n - dict.body_offset), dict,
                     static_cast<uint8_t *>(d_out), want, &produced, s, &tm);  // D3
     if (rc != ET_OK) return rc;
     tm.mark(3);
@@ -557,7 +557,7 @@ extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
         if (rc != ET_OK) return rc;
         if (body_bytes)
             ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, in + dict.body_offset, body_bytes, cudaMemcpyHostToDevice, s));
-        rc = unpack_dev(ctx, ctx->d_in, body_bytes, dict, ctx->d_out, want, &produced, s);
+        rc = unpack_dev(ctx, unpack_geometry(ctx->d_in, body_bytes), dict, ctx->d_out, want, &produced, s);
         if (rc != ET_OK) return rc;
         if (write_out) {
             if (produced == cap && dict.body_len > cap)
@@ -585,12 +585,33 @@ extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
     return ET_OK;
 }
 
-extern "C" int et_unpack_shard_dev(et_ctx *ctx, const void *d_body, size_t body_bytes, const et_dictionary *dict,
-                                   uint64_t entry_bit, uint64_t bit_end, uint64_t max_symbols, void *d_out, size_t cap,
-                                   uint64_t *n_symbols, uint64_t *exit_bit, void *stream) {
-    (void)d_body; (void)body_bytes; (void)dict; (void)entry_bit; (void)bit_end; (void)max_symbols;
-    (void)d_out; (void)cap; (void)n_symbols; (void)exit_bit; (void)stream;
-    return fail(ctx, ET_ERR_UNSUPPORTED, "sharded decode is not built yet");
+extern "C" int et_unpack_shard_dev(et_ctx *ctx, const void *d_range, size_t range_bytes, size_t own_begin_byte,
+                                   size_t own_end_byte, const et_dictionary *dict, int64_t head_bit, void *d_out, size_t cap,
+                                   uint64_t *n_symbols, uint64_t *entry_bit, uint64_t *exit_bit, void *stream) {
+    if (!ctx || !d_range || !dict || !n_symbols || (!d_out && cap)) return ET_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_range) & 15u) || (own_begin_byte & 31u) || own_begin_byte > own_end_byte ||
+        own_end_byte > range_bytes || (own_end_byte != range_bytes && ((own_end_byte & 31u) || own_end_byte + 32 > range_bytes)))
+        return fail(ctx, ET_ERR_INVALID_ARG, "shard geometry: 16-byte aligned range, 32-byte aligned owned part, 32 bytes of look-ahead");
+    if (head_bit >= 0 && ((uint64_t)head_bit < own_begin_byte * 8 || (uint64_t)head_bit >= own_begin_byte * 8 + 64))
+        return fail(ctx, ET_ERR_INVALID_ARG, "head_bit must lie in the first 64 bits of the owned part");
+    ET_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    StageTimer tm{ctx, s, true};
+    tm.mark(0);
+    tm.mark(1);
+    const UnpackGeometry g = unpack_geometry_shard(d_range, range_bytes, own_begin_byte, own_end_byte, (long long)head_bit);
+    uint64_t produced = 0;
+    uint32_t ee[2] = {0, 0};
+    const int rc = unpack_dev(ctx, g, *dict, static_cast<uint8_t *>(d_out), cap, &produced, s, &tm, ee);
+    if (rc != ET_OK) return rc;
+    tm.mark(3);
+    ET_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
+    tm.finish(4);
+    *n_symbols = produced;
+    // entry: bits past the first bit of the 32-byte sector grid the chunks are cut on (= own_begin: it is 32-byte aligned)
+    if (entry_bit) *entry_bit = (uint64_t)own_begin_byte * 8 + ee[0];
+    if (exit_bit) *exit_bit = (uint64_t)own_end_byte * 8 + ee[1];
+    return ET_OK;
 }
 
 // ====================================================================== synthetic inputs

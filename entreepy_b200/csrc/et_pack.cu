@@ -145,11 +145,12 @@ __device__ __forceinline__ bool tile_is_interior(const PackArgs &a, uint32_t til
 // ---- pass A: one CTA per group of tiles.  For every tile: the bits the earlier tiles of the
 // group emit; for the group: its total.  Streaming: 16 B per thread, 16 byte-table lookups.
 __global__ void __launch_bounds__(kPackThreads) tile_bits_kernel(const PackArgs a) {
-    __shared__ uint32_t len_sh[256];
+    __shared__ uint32_t len_sh[256 * 32];  // [sym][lane]: a warp-wide lookup never has a bank conflict
     __shared__ uint32_t warp_sum[2][kWarps];
-    len_sh[threadIdx.x] = static_cast<const uint2 *>(a.tables)[threadIdx.x].y;
+    for (int i = threadIdx.x; i < 256 * 32; i += kPackThreads) len_sh[i] = static_cast<const uint2 *>(a.tables)[i >> 5].y;
     __syncthreads();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t *len_lane = reinterpret_cast<const uint8_t *>(len_sh) + lane * 4;
     const uint32_t t_lo = blockIdx.x * a.group_tiles, t_hi = min(t_lo + a.group_tiles, a.num_tiles);
     uint32_t run = 0;  // bits of the group so far (same value in every thread)
     for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
@@ -158,16 +159,20 @@ __global__ void __launch_bounds__(kPackThreads) tile_bits_kernel(const PackArgs 
             const uint4 raw = ld_stream_v4(a.in_aligned + (uint64_t)tile * kPackTileSyms + (uint64_t)tid * kPackItems);
             const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                bits += len_sh[rw[q] & 0xffu] + len_sh[(rw[q] >> 8) & 0xffu] + len_sh[(rw[q] >> 16) & 0xffu] +
-                        len_sh[rw[q] >> 24];
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t w = rw[q];  // byte -> byte offset sym*128 into this lane's column
+                bits += *reinterpret_cast<const uint32_t *>(len_lane + ((w << 7) & 0x7f80u)) +
+                        *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 1) & 0x7f80u)) +
+                        *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 9) & 0x7f80u)) +
+                        *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 17) & 0x7f80u));
+            }
         } else {
             uint32_t valid;
             const uint4 raw = load_symbols(a, tile, tid, false, &valid);
             const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
             for (int i = 0; i < kPackItems; ++i) {
-                const uint32_t len = len_sh[(rw[i >> 2] >> (8 * (i & 3))) & 0xffu];
+                const uint32_t len = len_sh[((rw[i >> 2] >> (8 * (i & 3))) & 0xffu) * 32];
                 bits += ((valid >> i) & 1u) ? len : 0u;
             }
         }

@@ -1,14 +1,29 @@
-"""One .et stream across the GPUs of a box: contiguous byte ranges, three tiny exchanges.
+"""One .et stream across the GPUs of a box: contiguous byte ranges, tiny exchanges.
 
-world == 1 goes straight to et_encode_dev / et_decode_dev.  world > 1 is built on the shard
-entry points of the C ABI plus torch.distributed for the 2 KiB histogram all-reduce and the
-bit-offset / symbol-count all-gathers; bulk data never leaves its GPU.
+Encode: rank r packs text bytes [lo_r, hi_r).  Exchanges: histogram all-reduce (2 KiB), all-gather of
+one bit count per rank (the cross-GPU exclusive scan of bit offsets), all-gather of one seam byte per
+rank.  Every rank builds the same codebook from the reduced histogram (the host step is deterministic)
+and packs its slice directly at its final bit position; bulk data never leaves its GPU.
+
+Decode: rank r decodes body bytes [B_r, B_{r+1}) (32-byte aligned cuts).  The stream has no index, so a
+rank other than 0 does not know where its first codeword starts: it synchronises on the 64 bytes before
+its range and reports the boundary it found; one all-gather of (symbols, entry, exit) per rank lets every
+rank check entry_r == exit_{r-1}.  A rank whose guess was wrong (slowly synchronising codes) decodes again
+from the true boundary; this repeats at most world-1 times.  Symbol counts give the output offsets.
+
+The compute goes through a backend with three calls (histogram, pack_shard, unpack_shard): GpuBackend
+binds them to the C ABI (et_histogram_dev, et_pack_shard_dev, et_unpack_shard_dev); the CPU tests plug in
+an oracle-based stand-in to exercise this host logic over gloo.
 """
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 
 from . import _abi
+from .codec import build_codebook, parse_header, write_header
+
+LEAD_IN = 64     # bytes before a decode shard used to find its first codeword boundary
+LOOK_AHEAD = 32  # bytes after a decode shard (a codeword that begins inside it may end there)
 
 
 class ShardPlan:
@@ -22,41 +37,227 @@ class ShardPlan:
         self.n_local = self.hi - self.lo
 
 
+def body_cuts(body_bytes, world):
+    """Decode shard boundaries B_0..B_world: equal parts of the body, cut on 32-byte sectors.  Every cut but
+    the last leaves at least LOOK_AHEAD bytes after it (short bodies give the later ranks nothing)."""
+    last_cut = ((body_bytes - LOOK_AHEAD) & ~31) if body_bytes >= LOOK_AHEAD else 0
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(max(cuts[-1], min(last_cut, (r * body_bytes // world) & ~31)))
+    cuts.append(body_bytes)
+    return cuts
+
+
 @dataclass
 class EncodeResult:
-    total_bytes: int        # size of the whole .et file
-    local_bytes: int        # bytes of it resident in this rank's output buffer
-    header_bytes: int = 0
-    body_bit_offset: int = 0  # global bit offset of this rank's first code inside the body
-    body_bits: int = 0        # bits this rank produced
+    total_bytes: int                 # size of the whole .et file
+    header: bytes = b""              # the same on every rank
+    bit_offsets: list = field(default_factory=list)  # [world + 1] global bit offset of each rank's first code in the body
+    first_byte: int = 0              # body byte index of this rank's out[0]
+    local_bytes: int = 0             # bytes this rank wrote (out[0 : local_bytes])
+    own_lo: int = 0                  # body bytes [own_lo, own_hi) are final in this rank's buffer
+    own_hi: int = 0
+    codebook: object = None
+
+    @property
+    def body_bytes(self):
+        return (self.bit_offsets[-1] + 7) // 8
+
+
+@dataclass
+class DecodeResult:
+    n_local: int      # valid symbols in this rank's output buffer
+    offset: int       # position of the first of them in the text
+    rounds: int = 1   # 1 = every rank's guessed entry was right
+
+
+class Comm:
+    """The three exchanges, over torch.distributed (nccl: tensors on the GPU, gloo: on the CPU)."""
+
+    def __init__(self, dist, device):
+        self.dist, self.device = dist, device
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+
+    def allreduce_counts(self, counts):
+        if self.world == 1:
+            return counts
+        import torch
+
+        t = torch.from_numpy(counts.astype(np.int64)).to(self.device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy().astype(np.uint64)
+
+    def allgather_ints(self, values):
+        """values: list of python ints (non-negative, < 2^63) -> [world][len(values)]."""
+        if self.world == 1:
+            return [list(values)]
+        import torch
+
+        t = torch.tensor(list(values), dtype=torch.int64, device=self.device)
+        out = torch.empty(self.world * len(values), dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(out, t)
+        return out.cpu().view(self.world, len(values)).tolist()
+
+    def all_to_all_bytes(self, send, send_splits, recv_splits):
+        """Uneven all-to-all of byte ranges (point-to-point pairs: works on nccl and gloo alike)."""
+        import torch
+
+        recv = torch.empty(int(sum(recv_splits)), dtype=torch.uint8, device=send.device)
+        ops, so, ro = [], 0, 0
+        for q in range(self.world):
+            ns, nr = int(send_splits[q]), int(recv_splits[q])
+            if q == self.rank:
+                if ns:
+                    recv[ro : ro + nr].copy_(send[so : so + ns])
+            else:
+                if ns:
+                    ops.append(self.dist.P2POp(self.dist.isend, send[so : so + ns], q))
+                if nr:
+                    ops.append(self.dist.P2POp(self.dist.irecv, recv[ro : ro + nr], q))
+            so, ro = so + ns, ro + nr
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+        return recv
+
+
+class GpuBackend:
+    """histogram / pack_shard / unpack_shard on CUDA tensors through the C ABI."""
+
+    def __init__(self, codec, stream=None):
+        self.codec, self.stream = codec, stream
+
+    def histogram(self, t_in, n):
+        return self.codec.histogram_dev(t_in.data_ptr(), n, self.stream)
+
+    def shard_bits(self, counts, cb):
+        return self.codec.shard_bits(counts, cb)
+
+    def pack_shard(self, t_in, n, cb, phase, bits, t_out):
+        return self.codec.pack_shard_dev(t_in.data_ptr(), n, cb, phase, bits, t_out.data_ptr(), t_out.numel(), self.stream)
+
+    def unpack_shard(self, t_range, range_bytes, own_begin, own_end, dictionary, head_bit, t_out):
+        return self.codec.unpack_shard_dev(t_range.data_ptr(), range_bytes, own_begin, own_end, dictionary, head_bit,
+                                           t_out.data_ptr(), t_out.numel(), self.stream)
+
+    def or_byte(self, t_buf, index, value):
+        if value:
+            t_buf[index] |= value
+
+    def first_byte(self, t_buf):
+        return int(t_buf[0].item())
 
 
 class ShardedCodec:
-    def __init__(self, codec, plan, dist=None):
-        self.codec, self.plan, self.dist = codec, plan, dist
-        if plan.world > 1 and dist is None:
-            raise ValueError("world > 1 needs torch.distributed")
+    def __init__(self, backend, plan, comm):
+        self.backend, self.plan, self.comm = backend, plan, comm
 
-    # ---- device-resident
-    def encode(self, d_in, d_out, cap, flags, stream=None):
-        if self.plan.world == 1:
-            size = self.codec.encode_dev(d_in, self.plan.n_local, d_out, cap, flags, stream)
-            return EncodeResult(total_bytes=size, local_bytes=size)
-        raise NotImplementedError("sharded encode")
+    # ------------------------------------------------------------------ encode
+    def encode(self, t_in, t_out):
+        """t_in: this rank's slice of the text; t_out: room for its part of the body (n_local + 16 bytes is
+        what the reference's 7200+n scratch bound guarantees).  Returns EncodeResult; the .et file is
+        header + the ranks' bodies[own_lo:own_hi] in rank order."""
+        p, be = self.plan, self.backend
+        local = be.histogram(t_in, p.n_local)                       # K1
+        counts = self.comm.allreduce_counts(local)                  # exchange 1: 2 KiB
+        cb = build_codebook(counts)                                 # same tables on every rank
+        header = write_header(cb, p.n_total)
+        bits = be.shard_bits(local, cb)
+        gathered = self.comm.allgather_ints([bits])                 # exchange 2: the cross-GPU scan of bit offsets
+        offs = [0]
+        for r in range(p.world):
+            offs.append(offs[-1] + gathered[r][0])
+        my_off = offs[p.rank]
+        nbytes = be.pack_shard(t_in, p.n_local, cb, my_off & 7, bits, t_out)   # K2 at the final bit position
+        res = EncodeResult(total_bytes=len(header) + (offs[-1] + 7) // 8, header=header, bit_offsets=offs,
+                           first_byte=my_off >> 3, local_bytes=nbytes, codebook=cb)
+        # exchange 3: the byte in which rank r ends may also hold the first bits of the ranks after it
+        if p.world > 1:
+            firsts = self.comm.allgather_ints([be.first_byte(t_out) if nbytes else 0])
+            last = (offs[p.rank + 1] - 1) >> 3 if bits else -1
+            merged = 0
+            for q in range(p.rank + 1, p.world):
+                if offs[q + 1] > offs[q] and (offs[q] & 7) and (offs[q] >> 3) == last:
+                    merged |= firsts[q][0]
+            if merged:
+                be.or_byte(t_out, last - res.first_byte, merged)
+        # bytes of the body that are final in this rank's buffer: a shard that starts inside a byte leaves
+        # that byte to the rank that started it
+        lo = (my_off + 7) >> 3 if p.rank > 0 else 0
+        hi = (offs[p.rank + 1] + 7) >> 3
+        res.own_lo, res.own_hi = min(lo, hi), hi
+        return res
 
-    def decode(self, res, d_et, d_out, cap, flags, stream=None):
-        if self.plan.world == 1:
-            return self.codec.decode_dev(d_et + 4, res.total_bytes - 4, d_out, cap, flags, stream)
-        raise NotImplementedError("sharded decode")
+    # ------------------------------------------------------------------ body redistribution (setup for decode)
+    def decode_ranges(self, body_bytes):
+        cuts = body_cuts(body_bytes, self.plan.world)
+        ranges = []
+        for r in range(self.plan.world):
+            s = max(cuts[r] - LEAD_IN, 0) if r > 0 else 0
+            t = min(cuts[r + 1] + LOOK_AHEAD, body_bytes) if r + 1 < self.plan.world else body_bytes
+            ranges.append((s, t))
+        return cuts, ranges
 
-    # ---- host buffers (the reference-facing calls)
-    def encode_host(self, h_in, h_out, flags):
-        if self.plan.world == 1:
-            size = self.codec.encode_into(h_in, h_out, flags)
-            return size, EncodeResult(total_bytes=size, local_bytes=size)
-        raise NotImplementedError("sharded encode")
+    def scatter_body(self, res, t_body):
+        """From the layout encode() leaves (rank q holds body bytes [own_lo, own_hi)) to the layout decode()
+        wants (rank r holds [S_r, T_r): its equal share plus lead-in and look-ahead).  One all-to-all; this is
+        the job a file reader does when the stream comes from disk, so it is not part of the decode."""
+        import torch
 
-    def decode_host(self, res, h_et, h_out, flags):
-        if self.plan.world == 1:
-            return self.codec.decode_into(h_et[4 : res.total_bytes], h_out, flags)
-        raise NotImplementedError("sharded decode")
+        p = self.plan
+        cuts, ranges = self.decode_ranges(res.body_bytes)
+        if p.world == 1:
+            return t_body[: res.body_bytes]
+        owns = self.comm.allgather_ints([res.own_lo, res.own_hi])
+        send_parts, send_splits, recv_splits = [], [], []
+        for r in range(p.world):
+            lo, hi = max(res.own_lo, ranges[r][0]), min(res.own_hi, ranges[r][1])
+            n = max(hi - lo, 0)
+            send_splits.append(n)
+            if n:
+                send_parts.append(t_body[lo - res.first_byte : hi - res.first_byte])
+            s, t = ranges[p.rank]
+            recv_splits.append(max(min(owns[r][1], t) - max(owns[r][0], s), 0))
+        send = torch.cat(send_parts) if send_parts else torch.empty(0, dtype=torch.uint8, device=t_body.device)
+        return self.comm.all_to_all_bytes(send, send_splits, recv_splits)
+
+    # ------------------------------------------------------------------ decode
+    def decode(self, header, body_bytes, t_range, t_out):
+        """header: the .et bytes after the magic up to the body (every rank reads them); t_range: this rank's
+        range of the body as decode_ranges() lays it out; t_out: room for its text (any rank may get up to
+        8 symbols per byte in theory; the bench sizes it from the plan)."""
+        p, be = self.plan, self.backend
+        dictionary = parse_header(header)
+        cuts, ranges = self.decode_ranges(body_bytes)
+        s, t = ranges[p.rank]
+        own_begin, own_end = cuts[p.rank] - s, cuts[p.rank + 1] - s
+        head_bit = 0 if p.rank == 0 else -1
+        rounds, redo = 0, True
+        n = entry = exit_ = 0
+        while True:
+            if redo:
+                n, entry, exit_ = be.unpack_shard(t_range, t - s, own_begin, own_end, dictionary, head_bit, t_out)   # K3-K5
+            rounds += 1
+            if p.world == 1:
+                return DecodeResult(n_local=min(n, int(dictionary.body_len)), offset=0, rounds=rounds)
+            # exchange: symbols, where my first codeword began, where my last one ended (bits past the cut)
+            info = self.comm.allgather_ints([n, entry - own_begin * 8, exit_ - own_end * 8])
+            wrong, prev_exit = [], 0  # rank 0 starts on bit 0 of the body
+            for r in range(p.world):
+                if cuts[r] == cuts[r + 1]:
+                    continue  # an empty share passes its neighbour's end on
+                if r > 0 and info[r][1] != prev_exit:
+                    wrong.append((r, prev_exit))
+                prev_exit = info[r][2]
+            if not wrong:
+                break
+            mine = [e for r, e in wrong if r == p.rank]
+            redo = bool(mine)
+            if redo:
+                head_bit = own_begin * 8 + mine[0]
+            if rounds > p.world + 1:
+                raise RuntimeError("sharded decode did not settle")  # cannot happen: rank r is right after r rounds
+        offset = sum(info[r][0] for r in range(p.rank))
+        valid = max(min(info[p.rank][0], int(dictionary.body_len) - offset), 0)
+        return DecodeResult(n_local=valid, offset=offset, rounds=rounds)

@@ -147,22 +147,30 @@ ET_API int et_decode_dev(et_ctx *ctx, const void *d_in_after_magic, size_t n, vo
                   uint32_t flags, void *stream);
 
 /* ------------------------------------------------------------------ sharded path */
-/* Encode shard: pack d_in[0..n) with `cb` so that its first code bit lands at bit
+/* One .et stream across several GPUs: each rank owns a contiguous byte range of the text
+ * (encode) or of the body (decode); the host exchanges only the 2 KiB histogram, one bit
+ * count and one byte per rank (encode) and three words per rank (decode).
+ *
+ * Encode shard: pack d_in[0..n) with `cb` so that its first code bit lands at bit
  * `bit_phase` (0..7) of d_out[0]; bits before it are left zero, so the seam byte of two
- * adjacent shards is the OR of their two copies.  *out_bytes = ceil((bit_phase+bits)/8). */
+ * adjacent shards is the OR of their two copies.  shard_bits = et_shard_bits(local counts, cb).
+ * *out_bytes = ceil((bit_phase + shard_bits) / 8). */
 ET_API int et_pack_shard_dev(et_ctx *ctx, const void *d_in, size_t n, const et_codebook *cb, uint32_t bit_phase,
-                      void *d_out, size_t cap, size_t *out_bytes, uint64_t *bits, void *stream);
+                      uint64_t shard_bits, void *d_out, size_t cap, size_t *out_bytes, void *stream);
 /* Bits a shard with these local counts occupies under `cb` (the cross-GPU scan input). */
 ET_API uint64_t et_shard_bits(const uint64_t counts[256], const et_codebook *cb);
-/* Decode shard: decode the body bit range [bit_begin, bit_end) of d_body (byte 0 of
- * d_body is byte 0 of the body).  Step 1 resolves where the first codeword at or after
- * bit_begin starts, given `entry_bit` = a known codeword boundary (< bit_begin, or
- * bit_begin itself for the first shard), and counts the symbols that START inside the
- * range; step 2 writes them to d_out[0..count).  *exit_bit = first codeword boundary
- * >= bit_end (the next shard's entry). */
-ET_API int et_unpack_shard_dev(et_ctx *ctx, const void *d_body, size_t body_bytes, const et_dictionary *dict,
-                        uint64_t entry_bit, uint64_t bit_end, uint64_t max_symbols, void *d_out, size_t cap,
-                        uint64_t *n_symbols, uint64_t *exit_bit, void *stream);
+/* Decode shard.  d_range (16-byte aligned) holds range_bytes of the body; the symbols that BEGIN
+ * in its bytes [own_begin_byte, own_end_byte) are decoded to d_out.  own_begin_byte is a multiple
+ * of 32; own_end_byte is a multiple of 32 followed by at least 32 bytes of look-ahead, or equals
+ * range_bytes when the stream ends there.  head_bit >= 0: bit (from d_range) of a known codeword
+ * boundary in the first 64 bits of the owned part; head_bit < 0: unknown — the decoder
+ * synchronises on the bytes before own_begin_byte (give it >= 32) and reports what it found.
+ * *entry_bit = where the first owned codeword began, *exit_bit = first codeword boundary at or
+ * after own_end_byte*8 (both from d_range): rank r's entry must equal rank r-1's exit, which the
+ * host checks after one all-gather; a rank whose entry was wrong calls again with head_bit. */
+ET_API int et_unpack_shard_dev(et_ctx *ctx, const void *d_range, size_t range_bytes, size_t own_begin_byte,
+                        size_t own_end_byte, const et_dictionary *dict, int64_t head_bit, void *d_out, size_t cap,
+                        uint64_t *n_symbols, uint64_t *entry_bit, uint64_t *exit_bit, void *stream);
 
 /* ------------------------------------------------------------------ synthetic inputs (bench/test utility) */
 /* out[i] = smallest s with thresholds[s] > (splitmix64(seed + first_index + i) >> 32);
