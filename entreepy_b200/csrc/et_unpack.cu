@@ -338,11 +338,21 @@ __device__ __forceinline__ Chunk chunk_of(const DecArgs &a, uint32_t c) {
 struct Pair {
     uint4 a, b;
 };
-__device__ __forceinline__ Pair load_pair_fast(const DecArgs &a, uint64_t pair) {
+// The raw load and the byte swap are kept apart on purpose: the next sector is requested a
+// whole sector of decoding before its first use, and nothing touches the loaded registers
+// (not even the swap) until then, so the load never stalls the walk.
+__device__ __forceinline__ Pair load_pair_raw(const DecArgs &a, uint64_t pair) {
     Pair p;
-    p.a = load_piece_fast(a, 2 * pair);
-    p.b = load_piece_fast(a, 2 * pair + 1);
+    p.a = __ldg(reinterpret_cast<const uint4 *>(a.body_aligned) + 2 * pair);
+    p.b = __ldg(reinterpret_cast<const uint4 *>(a.body_aligned) + 2 * pair + 1);
     return p;
+}
+__device__ __forceinline__ uint4 swap4(uint4 v) { return make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w)); }
+__device__ __forceinline__ Pair swap_pair(const Pair &p) {
+    Pair q;
+    q.a = swap4(p.a);
+    q.b = swap4(p.b);
+    return q;
 }
 __device__ __forceinline__ void prefetch_chunk_l2(const DecArgs &a, const Chunk &k) {
     const uint8_t *p = a.body_aligned + (k.begin >> 3);
@@ -360,22 +370,23 @@ __device__ __forceinline__ uint32_t count_chunk_fast(const DecArgs &a, const Chu
     prefetch_chunk_l2(a, k);
     uint32_t w[5];
     uint32_t c = start;
-    Pair cur = load_pair_fast(a, pair0);
+    Pair raw = load_pair_raw(a, pair0);
     if (warm) {  // only the position survives the run-up; it stops on the first boundary inside the chunk
         const uint4 pre = load_piece_fast(a, 2 * pair0 - 1);
-        w[0] = pre.x; w[1] = pre.y; w[2] = pre.z; w[3] = pre.w; w[4] = cur.a.x;
+        w[0] = pre.x; w[1] = pre.y; w[2] = pre.z; w[3] = pre.w; w[4] = bswap32(raw.a.x);
         c = count_piece<true>(w, 0u, clut_s, a.wlut, a.nodes) & kPosMask;
     }
     *entry = c;
 #pragma unroll 1
     for (uint32_t p = 0; p + 1 < n_pairs; ++p) {
-        const Pair nxt = load_pair_fast(a, pair0 + p + 1);
+        const Pair cur = swap_pair(raw);
+        raw = load_pair_raw(a, pair0 + p + 1);
         w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
         c = count_piece<false>(w, c, clut_s, a.wlut, a.nodes);
-        w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = nxt.a.x;
+        w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = bswap32(raw.a.x);
         c = count_piece<false>(w, c, clut_s, a.wlut, a.nodes);
-        cur = nxt;
     }
+    const Pair cur = swap_pair(raw);
     const uint4 nxt = load_piece_fast(a, 2 * (pair0 + n_pairs));
     w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
     c = count_piece<false>(w, c, clut_s, a.wlut, a.nodes);
@@ -383,7 +394,7 @@ __device__ __forceinline__ uint32_t count_chunk_fast(const DecArgs &a, const Chu
     return count_piece<true>(w, c, clut_s, a.wlut, a.nodes);
 }
 
-__global__ void __launch_bounds__(kChunkThreads, 8) chunk_sync_kernel(const DecArgs a, int round) {
+__global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecArgs a, int round) {
     __shared__ __align__(16) uint32_t clut_sh[kLutSize];
     const uint32_t c = blockIdx.x * kChunkThreads + threadIdx.x;
     uint32_t start = 0;
@@ -511,16 +522,17 @@ __global__ void __launch_bounds__(kChunkThreads) chunk_write_kernel(const DecArg
         const uint32_t wlut_s = smem_addr(wlut_sh);
         prefetch_chunk_l2(a, k);
         uint32_t w[5];
-        Pair cur = load_pair_fast(a, pair0);
+        Pair raw = load_pair_raw(a, pair0);
 #pragma unroll 1
         for (uint32_t p = 0; p + 1 < n_pairs; ++p) {
-            const Pair nxt = load_pair_fast(a, pair0 + p + 1);
+            const Pair cur = swap_pair(raw);
+            raw = load_pair_raw(a, pair0 + p + 1);
             w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
             s = write_piece<false>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
-            w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = nxt.a.x;
+            w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = bswap32(raw.a.x);
             s = write_piece<false>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
-            cur = nxt;
         }
+        const Pair cur = swap_pair(raw);
         const uint4 nxt = load_piece_fast(a, 2 * (pair0 + n_pairs));
         w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
         s = write_piece<false>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
