@@ -146,44 +146,68 @@ __device__ __forceinline__ bool tile_is_interior(const PackArgs &a, uint32_t til
 // group emit; for the group: its total.  Streaming: 16 B per thread, 16 byte-table lookups.
 __global__ void __launch_bounds__(kPackThreads) tile_bits_kernel(const PackArgs a) {
     __shared__ uint32_t len_sh[256 * 32];  // [sym][lane]: a warp-wide lookup never has a bank conflict
-    __shared__ uint32_t warp_sum[2][kWarps];
+    __shared__ uint32_t warp_sum[2][4 * kWarps];
     for (int i = threadIdx.x; i < 256 * 32; i += kPackThreads) len_sh[i] = static_cast<const uint2 *>(a.tables)[i >> 5].y;
     __syncthreads();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t *len_lane = reinterpret_cast<const uint8_t *>(len_sh) + lane * 4;
     const uint32_t t_lo = blockIdx.x * a.group_tiles, t_hi = min(t_lo + a.group_tiles, a.num_tiles);
     uint32_t run = 0;  // bits of the group so far (same value in every thread)
-    for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
-        uint32_t bits = 0;
-        if (tile_is_interior(a, tile)) {
-            const uint4 raw = ld_stream_v4(a.in_aligned + (uint64_t)tile * kPackTileSyms + (uint64_t)tid * kPackItems);
-            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+    constexpr int kBatch = 4;  // tiles per iteration: four independent 16-byte loads in flight per thread
+    for (uint32_t t0 = t_lo; t0 < t_hi; t0 += kBatch) {
+        uint4 raw[kBatch];
+        uint32_t valid[kBatch];
+        bool interior[kBatch];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t w = rw[q];  // byte -> byte offset sym*128 into this lane's column
-                bits += *reinterpret_cast<const uint32_t *>(len_lane + ((w << 7) & 0x7f80u)) +
-                        *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 1) & 0x7f80u)) +
-                        *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 9) & 0x7f80u)) +
-                        *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 17) & 0x7f80u));
-            }
-        } else {
-            uint32_t valid;
-            const uint4 raw = load_symbols(a, tile, tid, false, &valid);
-            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int i = 0; i < kPackItems; ++i) {
-                const uint32_t len = len_sh[((rw[i >> 2] >> (8 * (i & 3))) & 0xffu) * 32];
-                bits += ((valid >> i) & 1u) ? len : 0u;
+        for (int b = 0; b < kBatch; ++b) {
+            const uint32_t tile = t0 + b;
+            interior[b] = tile < t_hi && tile_is_interior(a, tile);
+            valid[b] = 0xffffu;
+            if (interior[b])
+                raw[b] = ld_stream_v4(a.in_aligned + (uint64_t)tile * kPackTileSyms + (uint64_t)tid * kPackItems);
+            else if (tile < t_hi)
+                raw[b] = load_symbols(a, tile, tid, false, &valid[b]);
+            else {
+                raw[b] = make_uint4(0, 0, 0, 0);
+                valid[b] = 0;
             }
         }
+        uint32_t bits[kBatch];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
-        uint32_t *ws = warp_sum[(tile - t_lo) & 1];  // double-buffered: one barrier per tile
-        if (lane == 0) ws[warp] = bits;
+        for (int b = 0; b < kBatch; ++b) {
+            const uint32_t rw[4] = {raw[b].x, raw[b].y, raw[b].z, raw[b].w};
+            bits[b] = 0;
+            if (interior[b]) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t w = rw[q];  // byte -> byte offset sym*128 into this lane's column
+                    bits[b] += *reinterpret_cast<const uint32_t *>(len_lane + ((w << 7) & 0x7f80u)) +
+                               *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 1) & 0x7f80u)) +
+                               *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 9) & 0x7f80u)) +
+                               *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 17) & 0x7f80u));
+                }
+            } else if (valid[b]) {
+#pragma unroll
+                for (int i = 0; i < kPackItems; ++i) {
+                    const uint32_t len = len_sh[((rw[i >> 2] >> (8 * (i & 3))) & 0xffu) * 32];
+                    bits[b] += ((valid[b] >> i) & 1u) ? len : 0u;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], o);
+        }
+        uint32_t *ws = warp_sum[((t0 - t_lo) / kBatch) & 1];  // double-buffered: one barrier per batch
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) ws[b * kWarps + warp] = bits[b];
+        }
         __syncthreads();
-        if (tid == 0) a.tile_bits[tile] = run;
 #pragma unroll
-        for (int q = 0; q < kWarps; ++q) run += ws[q];
+        for (int b = 0; b < kBatch; ++b) {
+            if (tid == 0 && t0 + b < t_hi) a.tile_bits[t0 + b] = run;
+#pragma unroll
+            for (int q = 0; q < kWarps; ++q) run += ws[b * kWarps + q];
+        }
     }
     if (tid == 0) a.group_prefix[blockIdx.x] = run;  // group total; group_scan_kernel turns it into a prefix
 }
@@ -230,11 +254,17 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
     __syncthreads();
     const uint8_t *table_lane = table + (lane & (kTableLanes - 1)) * 8;
 
+    // the next tile's 16 bytes are requested a whole tile ahead, so their DRAM latency is never waited for
+    uint32_t valid_next = 0xffffu;
+    uint4 raw_next = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x < a.num_tiles) raw_next = load_symbols(a, blockIdx.x, tid, tile_is_interior(a, blockIdx.x), &valid_next);
     for (uint32_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         // ---- (1) load + lookup
         const bool interior = tile_is_interior(a, tile);  // uniform over the CTA
-        uint32_t valid;
-        const uint4 raw = load_symbols(a, tile, tid, interior, &valid);
+        const uint32_t valid = valid_next;
+        const uint4 raw = raw_next;
+        if (tile + gridDim.x < a.num_tiles)
+            raw_next = load_symbols(a, tile + gridDim.x, tid, tile_is_interior(a, tile + gridDim.x), &valid_next);
         const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
         uint32_t pair_code[kPairs], pair_len[kPairs];
         uint32_t my_bits = 0;
