@@ -33,7 +33,6 @@ namespace et {
 namespace {
 
 constexpr uint32_t kPosMask = 0x1ffu;  // position field of a packed walk state (bit 8 = marker)
-constexpr int kRowStride = 80;         // staging row per thread: up to 31 + 34 pending bytes, 16-byte aligned
 
 struct DecArgs {
     const uint8_t *body_aligned;
@@ -77,19 +76,8 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void sts_u8_1(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u8 [%0+1], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------ long codes
@@ -158,44 +146,69 @@ __device__ __forceinline__ uint32_t count_piece(const uint32_t (&w)[5], uint32_t
     return c;
 }
 
-// Output side of the write walk: a private row in shared memory, flushed to global memory as
-// aligned 32-byte sectors (whole sectors: the text in flight on the GPU is larger than L2, so
-// a half-written sector would go to DRAM twice).  Row byte k <-> gblock[k]; the first sector
-// may begin with bytes that belong to the previous chunk (head_skip of them) and is then
-// stored bytewise.
-struct OutRow {
-    uint32_t row_s;
-    uint8_t *gblock;
+// Output side of the write walk.  Decoded symbols are shifted into a 64-bit register (newest
+// byte on top).  Every fourth symbol the finished 32-bit word is stored, under a predicate (no
+// branch, so the lanes of a warp stay together), into the thread's ring of 16 words in shared
+// memory: word m of lane L sits at ring + ((m + 1) & 15) * 128 + L * 4, so a lane only ever
+// touches its own bank and neither these stores nor the loads of the flush can conflict.
+// Where the lanes of a warp meet again anyway (the end of each 32-bit stream word) whole 32-byte
+// sectors leave for global memory (whole sectors: the text in flight on the GPU is larger than
+// L2, a half-written sector would go to DRAM twice).
+// The symbol count n in the walk state doubles as the byte index from the sector grid of the
+// destination: it starts at head_skip, the bytes of the first sector that belong to the chunk
+// before.  Ring capacity: after a flush fewer than 32 bytes are pending and one stream word
+// yields at most 33 symbols (32 one-bit codes plus the second symbol of the last window), so
+// at most 64 bytes = 16 words are ever pending.
+struct OutRing {
+    uint32_t ring_s;   // shared address of this lane's slot 0
+    uint8_t *gsector;  // global address of the sector being assembled (32-byte aligned)
     uint32_t head_skip;
+    uint32_t lo, hi;   // the last 8 symbols, newest in the top byte of hi
+    uint32_t stored;   // sectors that have left for global memory
 };
 
-__device__ __forceinline__ uint32_t flush_row(uint32_t c, OutRow &r) {
-    const uint32_t fill = (c >> 9) - r.row_s;
-    const uint32_t nblk = fill >> 5;
-    if (nblk == 0) return c;
-    for (uint32_t b = 0; b < nblk; ++b) {
-        const uint32_t s = r.row_s + 32u * b;
-        const uint4 v0 = lds_v4(s), v1 = lds_v4(s + 16);
+// shared address of word m of the ring, given (m + 1) in bits 11+ of a walk state
+__device__ __forceinline__ uint32_t ring_slot_after(const OutRing &r, uint32_t c) { return ((c >> 4) & 0x780u) + r.ring_s; }
+__device__ __forceinline__ uint32_t ring_slot(const OutRing &r, uint32_t m) { return (((m + 1u) & 15u) << 7) + r.ring_s; }
+
+// Append `syms` (1 or 2 symbols in its low bytes; shift = 8 or 16; shift 0 appends nothing) and
+// advance the walk state by `add` (bits | symbols << 9).
+__device__ __forceinline__ uint32_t emit(uint32_t c, OutRing &r, uint32_t syms, uint32_t shift, uint32_t add) {
+    r.lo = __funnelshift_r(r.lo, r.hi, shift);
+    r.hi = __funnelshift_r(r.hi, syms, shift);
+    const uint32_t before = c;
+    c += add;
+    // the symbol count crossed a multiple of 4: a word is complete (one symbol of the next word may sit on top of it)
+    const uint32_t crossed = (before ^ c) & (4u << 9);
+    const uint32_t w = (c & (1u << 9)) ? __funnelshift_r(r.lo, r.hi, 24) : r.hi;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t}" ::"r"(crossed),
+        "r"(ring_slot_after(r, c)), "r"(w)
+        : "memory");
+    return c;
+}
+
+// End of a stream word: finished sectors leave together.
+__device__ __forceinline__ void flush_sectors(uint32_t c, OutRing &r) {
+    while (((c >> 14) & 0x3ffffu) > r.stored) {
+        const uint32_t m0 = r.stored * 8u;  // first word of the sector; 8 consecutive slots, wrapping at 16
         if (r.head_skip) {  // first sector of the chunk: its leading bytes belong to the chunk before
-            (void)v0; (void)v1;
-            for (uint32_t j = r.head_skip; j < 32u; ++j) r.gblock[j] = (uint8_t)lds_u8(s + j);
+            for (uint32_t k = r.head_skip; k < 32u; ++k) r.gsector[k] = (uint8_t)lds_u8(ring_slot(r, m0 + (k >> 2)) + (k & 3u));
             r.head_skip = 0;
         } else {
-            *reinterpret_cast<uint4 *>(r.gblock) = v0;
-            *reinterpret_cast<uint4 *>(r.gblock + 16) = v1;
+            uint32_t v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = lds_u32(ring_slot(r, m0 + i));
+            *reinterpret_cast<uint4 *>(r.gsector) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4 *>(r.gsector + 16) = make_uint4(v[4], v[5], v[6], v[7]);
         }
-        r.gblock += 32;
+        r.gsector += 32;
+        r.stored += 1;
     }
-    // the unfinished sector moves to the front of the row
-    const uint32_t s = r.row_s + 32u * nblk;
-    const uint4 l0 = lds_v4(s), l1 = lds_v4(s + 16);
-    sts_v4(r.row_s, l0);
-    sts_v4(r.row_s + 16, l1);
-    return c - ((32u * nblk) << 9);
 }
 
 template <bool LAST>
-__device__ __forceinline__ uint32_t write_piece(const uint32_t (&w)[5], uint32_t c, uint32_t wlut_s, OutRow &r,
+__device__ __forceinline__ uint32_t write_piece(const uint32_t (&w)[5], uint32_t c, uint32_t wlut_s, OutRing &r,
                                                 const uint32_t *__restrict__ clut, const uint32_t *__restrict__ wlut,
                                                 const uint32_t *__restrict__ nodes, uint32_t *bad) {
 #pragma unroll
@@ -205,18 +218,12 @@ __device__ __forceinline__ uint32_t write_piece(const uint32_t (&w)[5], uint32_t
             if (!LAST || wi < 3) {
                 while (!(c & 0x1e0u)) {
                     const uint32_t e = lds_u32(wlut_s + window_offset(hi, lo, c));
-                    const uint32_t o = c >> 9;
-                    sts_u8(o, e);  // a marker entry stores one garbage byte that the long code's symbol overwrites
-                    if (e & (2u << 25)) sts_u8_1(o, e >> 8);
-                    c += e >> 16;
+                    c = emit(c, r, e, (e >> 22) & 0x18u, e >> 16);  // a marker entry appends nothing and sets bit 8
                 }
             } else {
                 while ((c & kPosMask) <= (uint32_t)(32 - kLutBits)) {
                     const uint32_t e = lds_u32(wlut_s + window_offset(hi, lo, c));
-                    const uint32_t o = c >> 9;
-                    sts_u8(o, e);
-                    if (e & (2u << 25)) sts_u8_1(o, e >> 8);
-                    c += e >> 16;
+                    c = emit(c, r, e, (e >> 22) & 0x18u, e >> 16);
                 }
                 while (!(c & 0x1e0u)) {  // one symbol at a time up to the chunk's last bit
                     const uint32_t off = window_offset(hi, lo, c);
@@ -225,18 +232,17 @@ __device__ __forceinline__ uint32_t write_piece(const uint32_t (&w)[5], uint32_t
                         c |= kLutMarker;
                         break;
                     }
-                    sts_u8(c >> 9, lds_u32(wlut_s + off));
-                    c += a;
+                    c = emit(c, r, lds_u32(wlut_s + off), 8u, a);
                 }
             }
             if (!(c & kLutMarker)) break;
             uint32_t sym = 0;
             const uint32_t add = long_code_add(hi, lo, c, wlut, nodes, &sym, bad);
-            if (add != 1u) sts_u8(c >> 9, sym);
-            c += add - kLutMarker;
+            c -= kLutMarker;
+            c = (add != 1u) ? emit(c, r, sym, 8u, add) : c + 1u;
         }
         c -= 32u;
-        c = flush_row(c, r);  // at most 31 + 34 bytes are pending here: the row holds 80
+        flush_sectors(c, r);
     }
     return c;
 }
@@ -482,9 +488,9 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const DecArgs a, uint3
 }
 
 // ------------------------------------------------------------------ write
-__global__ void __launch_bounds__(kChunkThreads) chunk_write_kernel(const DecArgs a) {
+__global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const DecArgs a) {
     __shared__ __align__(16) uint32_t wlut_sh[kLutSize];
-    __shared__ __align__(16) uint8_t rows[kChunkThreads * kRowStride];
+    __shared__ __align__(16) uint32_t rings[(kChunkThreads / 32) * 16 * 32];  // per warp: 16 words x 32 lanes
     __shared__ uint32_t warp_sum[kChunkThreads / 32];
     for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) wlut_sh[i] = a.wlut[i];
 
@@ -511,12 +517,14 @@ __global__ void __launch_bounds__(kChunkThreads) chunk_write_kernel(const DecArg
     uint32_t bad = 0;
     if (k.interior && o + cnt <= a.max_symbols) {
         uint8_t *dst = a.out + o;
-        OutRow r;
-        r.row_s = smem_addr(rows + tid * kRowStride);
+        OutRing r;
+        r.ring_s = smem_addr(rings) + warp * 2048u + lane * 4u;
         r.head_skip = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 31u);
-        r.gblock = dst - r.head_skip;
+        r.gsector = dst - r.head_skip;
+        r.lo = r.hi = 0;
+        r.stored = 0;
         const uint32_t head = r.head_skip;
-        uint32_t s = start | ((r.row_s + r.head_skip) << 9);
+        uint32_t s = start | (head << 9);
         const uint64_t pair0 = k.begin >> 8;
         const uint32_t n_pairs = a.chunk_bytes >> 5;
         const uint32_t wlut_s = smem_addr(wlut_sh);
@@ -538,9 +546,11 @@ __global__ void __launch_bounds__(kChunkThreads) chunk_write_kernel(const DecArg
         s = write_piece<false>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
         w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = nxt.x;
         s = write_piece<true>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
-        // what is left in the row is less than a sector: bytewise (head_skip is still set when no sector ever left)
-        const uint32_t fill = (s >> 9) - r.row_s;
-        for (uint32_t j = r.head_skip ? head : 0u; j < fill; ++j) r.gblock[j] = rows[tid * kRowStride + j];
+        // the unfinished word goes to the ring, then what is left of the last sector leaves bytewise
+        const uint32_t n_end = s >> 9;  // bytes from the sector grid, head included
+        if (n_end & 3u) sts_u32(ring_slot(r, n_end >> 2), r.hi >> (8u * (4u - (n_end & 3u))));
+        for (uint32_t kk = r.head_skip ? head : (n_end & ~31u); kk < n_end; ++kk)
+            r.gsector[kk & 31u] = (uint8_t)lds_u8(ring_slot(r, kk >> 2) + (kk & 3u));
     } else {
         uint32_t n = 0;
         if (k.begin + start < k.end) walk_generic<true>(a, k.begin + start, k.end, a.end_bit, &n, o, &bad);
