@@ -124,14 +124,15 @@ __device__ __forceinline__ uint32_t long_code_add(uint32_t hi, uint32_t lo, uint
 // chunk, so only symbols that BEGIN before its last bit may be consumed: in the last word a
 // multi-symbol window is used only while it cannot cross that bit, then single symbols.
 // Returns c relative to the first word of the next piece.
-template <bool LAST>
-__device__ __forceinline__ uint32_t count_piece(const uint32_t (&w)[5], uint32_t c, uint32_t clut_s,
+// (`last` is a run-time flag so that the body exists once: eight inlined copies of these loops
+// did not fit the instruction cache.)
+__device__ __forceinline__ uint32_t count_piece(const uint32_t (&w)[5], uint32_t c, bool last, uint32_t clut_s,
                                                 const uint32_t *__restrict__ wlut, const uint32_t *__restrict__ nodes) {
 #pragma unroll
     for (int wi = 0; wi < 4; ++wi) {
         const uint32_t hi = w[wi], lo = w[wi + 1];
         for (;;) {
-            if (!LAST || wi < 3) {
+            if (wi < 3 || !last) {
                 while (!(c & 0x1e0u)) c += lds_u16(clut_s + window_offset(hi, lo, c));
             } else {
                 while ((c & kPosMask) <= (uint32_t)(32 - kLutBits)) c += lds_u16(clut_s + window_offset(hi, lo, c));
@@ -207,15 +208,14 @@ __device__ __forceinline__ void flush_sectors(uint32_t c, OutRing &r) {
     }
 }
 
-template <bool LAST>
-__device__ __forceinline__ uint32_t write_piece(const uint32_t (&w)[5], uint32_t c, uint32_t wlut_s, OutRing &r,
+__device__ __forceinline__ uint32_t write_piece(const uint32_t (&w)[5], uint32_t c, bool last, uint32_t wlut_s, OutRing &r,
                                                 const uint32_t *__restrict__ clut, const uint32_t *__restrict__ wlut,
                                                 const uint32_t *__restrict__ nodes, uint32_t *bad) {
 #pragma unroll
     for (int wi = 0; wi < 4; ++wi) {
         const uint32_t hi = w[wi], lo = w[wi + 1];
         for (;;) {
-            if (!LAST || wi < 3) {
+            if (wi < 3 || !last) {
                 while (!(c & 0x1e0u)) {
                     const uint32_t e = lds_u32(wlut_s + window_offset(hi, lo, c));
                     c = emit(c, r, e, (e >> 22) & 0x18u, e >> 16);  // a marker entry appends nothing and sets bit 8
@@ -376,28 +376,31 @@ __device__ __forceinline__ uint32_t count_chunk_fast(const DecArgs &a, const Chu
     prefetch_chunk_l2(a, k);
     uint32_t w[5];
     uint32_t c = start;
+    const uint32_t n_pieces = a.chunk_bytes >> 4;
+    (void)n_pairs;
     Pair raw = load_pair_raw(a, pair0);
     if (warm) {  // only the position survives the run-up; it stops on the first boundary inside the chunk
         const uint4 pre = load_piece_fast(a, 2 * pair0 - 1);
         w[0] = pre.x; w[1] = pre.y; w[2] = pre.z; w[3] = pre.w; w[4] = bswap32(raw.a.x);
-        c = count_piece<true>(w, 0u, clut_s, a.wlut, a.nodes) & kPosMask;
+        c = count_piece(w, 0u, true, clut_s, a.wlut, a.nodes) & kPosMask;
     }
     *entry = c;
+    Pair cur = raw;
 #pragma unroll 1
-    for (uint32_t p = 0; p + 1 < n_pairs; ++p) {
-        const Pair cur = swap_pair(raw);
-        raw = load_pair_raw(a, pair0 + p + 1);
-        w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
-        c = count_piece<false>(w, c, clut_s, a.wlut, a.nodes);
-        w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = bswap32(raw.a.x);
-        c = count_piece<false>(w, c, clut_s, a.wlut, a.nodes);
+    for (uint32_t p = 0; p < n_pieces; ++p) {
+        if (!(p & 1u)) {  // a new sector: swap the one that has arrived, request the next (the piece after the chunk at the end)
+            cur = swap_pair(raw);
+            if (p + 2 < n_pieces)
+                raw = load_pair_raw(a, pair0 + (p >> 1) + 1);
+            else
+                raw.a = __ldg(reinterpret_cast<const uint4 *>(a.body_aligned) + 2 * (pair0 + (p >> 1) + 1));
+            w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
+        } else {
+            w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = bswap32(raw.a.x);
+        }
+        c = count_piece(w, c, p + 1 == n_pieces, clut_s, a.wlut, a.nodes);
     }
-    const Pair cur = swap_pair(raw);
-    const uint4 nxt = load_piece_fast(a, 2 * (pair0 + n_pairs));
-    w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
-    c = count_piece<false>(w, c, clut_s, a.wlut, a.nodes);
-    w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = nxt.x;
-    return count_piece<true>(w, c, clut_s, a.wlut, a.nodes);
+    return c;
 }
 
 __global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecArgs a, int round) {
@@ -530,22 +533,24 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
         const uint32_t wlut_s = smem_addr(wlut_sh);
         prefetch_chunk_l2(a, k);
         uint32_t w[5];
+        const uint32_t n_pieces = a.chunk_bytes >> 4;
+        (void)n_pairs;
         Pair raw = load_pair_raw(a, pair0);
+        Pair cur = raw;
 #pragma unroll 1
-        for (uint32_t p = 0; p + 1 < n_pairs; ++p) {
-            const Pair cur = swap_pair(raw);
-            raw = load_pair_raw(a, pair0 + p + 1);
-            w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
-            s = write_piece<false>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
-            w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = bswap32(raw.a.x);
-            s = write_piece<false>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
+        for (uint32_t p = 0; p < n_pieces; ++p) {
+            if (!(p & 1u)) {  // a new sector: swap the one that has arrived, request the next (the piece after the chunk at the end)
+                cur = swap_pair(raw);
+                if (p + 2 < n_pieces)
+                    raw = load_pair_raw(a, pair0 + (p >> 1) + 1);
+                else
+                    raw.a = __ldg(reinterpret_cast<const uint4 *>(a.body_aligned) + 2 * (pair0 + (p >> 1) + 1));
+                w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
+            } else {
+                w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = bswap32(raw.a.x);
+            }
+            s = write_piece(w, s, p + 1 == n_pieces, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
         }
-        const Pair cur = swap_pair(raw);
-        const uint4 nxt = load_piece_fast(a, 2 * (pair0 + n_pairs));
-        w[0] = cur.a.x; w[1] = cur.a.y; w[2] = cur.a.z; w[3] = cur.a.w; w[4] = cur.b.x;
-        s = write_piece<false>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
-        w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = nxt.x;
-        s = write_piece<true>(w, s, wlut_s, r, a.clut, a.wlut, a.nodes, &bad);
         // the unfinished word goes to the ring, then what is left of the last sector leaves bytewise
         const uint32_t n_end = s >> 9;  // bytes from the sector grid, head included
         if (n_end & 3u) sts_u32(ring_slot(r, n_end >> 2), r.hi >> (8u * (4u - (n_end & 3u))));
