@@ -134,7 +134,7 @@ class Codec:
 
     @property
     def last_decode_rounds(self):
-        """Check rounds of the last decode (2: every guessed chunk entry was right; more: fixpoint rounds were needed)."""
+        """Passes over the chunk entries in the last decode (2: the guesses plus one repair round sufficed; more: fixpoint rounds were needed)."""
         return int(self._lib.et_ctx_last_decode_rounds(self._ctx))
 
     def last_stage_ms(self):

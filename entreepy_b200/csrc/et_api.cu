@@ -33,7 +33,7 @@ struct et_ctx {
     int out_fd = 1;
     uint64_t launches = 0;
     float stage_ms[4] = {0, 0, 0, 0};
-    uint32_t last_decode_rounds = 0;  // check rounds of the last decode (2 = every guessed entry was right)
+    uint32_t last_decode_rounds = 0;  // passes over the chunk entries in the last decode (2 = guesses + one repair round sufficed)
     char err[512] = {0};
 };
 

@@ -450,6 +450,8 @@ __global__ void __launch_bounds__(kChunkThreads) chunk_sum_kernel(const DecArgs 
     __shared__ uint32_t warp_sum[kChunkThreads / 32];
     const uint32_t c = blockIdx.x * kChunkThreads + threadIdx.x;
     uint32_t v = c < a.n_chunks ? a.count[c] : 0u;
+    // the check of the guessed entries rides along: does every chunk start where its left neighbour ended?
+    if (c > 0 && c < a.n_chunks && a.start_off[c] != a.exit_off[c - 1]) *a.changed = 1u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
@@ -651,28 +653,47 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.out = d_out;
     a.max_symbols = max_symbols;
 
+    // Common case (codes that re-synchronise quickly): one walk from the guesses, one repair
+    // round for the few chunks whose run-up was too short (text: 0.1 % of them; their exits do
+    // not move, because a walk that missed 128 bits of run-up still locks on inside 2048 bits of
+    // chunk), the final check fused into the block sums, the write walk — and a single look at
+    // the flag at the very end.  Only when that check failed (slowly synchronising codes) do
+    // the fixpoint rounds run, and the sums and the write walk are repeated.
     chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, 0);
-    if (launches) *launches += 1;
-    uint32_t rounds = 0;
+    chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, 1);
+    err = cudaMemsetAsync(a.changed, 0, 4, stream);
+    if (err != cudaSuccess) return err;
+    if (launches) *launches += 2;
+    uint32_t rounds = 2;
     for (;;) {
-        // two check rounds per host visit: the second finds nothing to do once the first settled everything
-        chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, (int)rounds + 1);
-        err = cudaMemsetAsync(a.changed, 0, 4, stream);
-        if (err != cudaSuccess) return err;
-        chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, (int)rounds + 2);
-        rounds += 2;
-        if (launches) *launches += 2;
+        chunk_sum_kernel<<<nb, kChunkThreads, 0, stream>>>(a);
+        chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, nb);
+        chunk_write_kernel<<<nb, kChunkThreads, 0, stream>>>(a);
+        if (launches) *launches += 3;
         err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream);
         if (err != cudaSuccess) return err;
         err = cudaStreamSynchronize(stream);
         if (err != cudaSuccess) return err;
-        if (*h_flag == 0) break;
-        if (rounds > n + 4u) return cudaErrorUnknown;  // cannot happen: each round settles one more chunk
+        if (*h_flag == 0) break;  // every entry was the true one: what the write walk produced stands
+        for (;;) {
+            // two check rounds per host visit: the second finds nothing to do once the first settled everything
+            chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, (int)rounds);
+            err = cudaMemsetAsync(a.changed, 0, 4, stream);
+            if (err != cudaSuccess) return err;
+            chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, (int)rounds + 1);
+            rounds += 2;
+            if (launches) *launches += 2;
+            err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream);
+            if (err != cudaSuccess) return err;
+            err = cudaStreamSynchronize(stream);
+            if (err != cudaSuccess) return err;
+            if (*h_flag == 0) break;
+            if (rounds > n + 4u) return cudaErrorUnknown;  // cannot happen: each round settles one more chunk
+        }
+        // the error flags the first write walk may have raised came from a wrong parse
+        err = cudaMemsetAsync(a.error_flags, 0, 4, stream);
+        if (err != cudaSuccess) return err;
     }
-    chunk_sum_kernel<<<nb, kChunkThreads, 0, stream>>>(a);
-    chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, nb);
-    chunk_write_kernel<<<nb, kChunkThreads, 0, stream>>>(a);
-    if (launches) *launches += 3;
     if (rounds_out) *rounds_out = rounds;
     return cudaGetLastError();
 }

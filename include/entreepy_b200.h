@@ -103,7 +103,7 @@ ET_API uint64_t et_ctx_kernel_launches(const et_ctx *ctx);
  * Only filled when ET_FLAG_TIMING or ET_FLAG_DEBUG was passed. */
 ET_API int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]);
 
-/* Check rounds of the last decode: 2 = every chunk's guessed entry was a true codeword boundary
+/* Passes over the chunk entries in the last decode: 2 = the guessed entries plus one repair round were enough
  * (self-synchronising streams); more = that many fixpoint rounds were needed (slowly synchronising codes). */
 ET_API uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx);
 
