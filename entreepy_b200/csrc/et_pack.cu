@@ -61,7 +61,9 @@ struct PackArgs {
     uint32_t *ticket;
     uint32_t *tile_bits;               // [num_tiles] bits of the earlier tiles of the same group (narrow path)
     unsigned long long *group_prefix;  // [n_groups] bits before each group of tiles
-    uint32_t group_tiles;              // tiles per group
+    uint32_t group_tiles;              // tiles per group (a power of two)
+    uint32_t group_shift;              // log2(group_tiles)
+    uint32_t interior_lo, interior_hi; // tiles [lo, hi) lie wholly inside the input
 };
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane) {
@@ -139,7 +141,7 @@ __device__ __forceinline__ uint4 load_symbols(const PackArgs &a, uint32_t tile, 
     return ld_partial_v4(a.in_aligned + v0, l, h);
 }
 __device__ __forceinline__ bool tile_is_interior(const PackArgs &a, uint32_t tile) {
-    return (uint64_t)tile * kPackTileSyms >= a.misalign && (uint64_t)(tile + 1) * kPackTileSyms <= a.v_end;
+    return tile >= a.interior_lo && tile < a.interior_hi;
 }
 
 // ---- pass A: one CTA per group of tiles.  For every tile: the bits the earlier tiles of the
@@ -269,24 +271,32 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
         uint32_t pair_code[kPairs], pair_len[kPairs];
         uint32_t my_bits = 0;
         bool slow = !interior;
+        if (interior) {
+            uint32_t longest = 0;
 #pragma unroll
-        for (int j = 0; j < kPairs; ++j) {
-            const uint32_t w = rw[j >> 1];
-            const int sa = 16 * (j & 1), sb = sa + 8;
-            // byte -> byte offset sym*128 into this lane's column of the table
-            const uint32_t oa = sa == 0 ? ((w << 7) & 0x7f80u) : ((w >> (sa - 7)) & 0x7f80u);
-            const uint32_t ob = (w >> (sb - 7)) & 0x7f80u;
-            uint2 ea = *reinterpret_cast<const uint2 *>(table_lane + oa);
-            uint2 eb = *reinterpret_cast<const uint2 *>(table_lane + ob);
-            if (!interior) {
-                if (!((valid >> (2 * j)) & 1u)) ea = make_uint2(0, 0);
-                if (!((valid >> (2 * j + 1)) & 1u)) eb = make_uint2(0, 0);
+            for (int j = 0; j < kPairs; ++j) {
+                const uint32_t w = rw[j >> 1];
+                const int sa = 16 * (j & 1), sb = sa + 8;
+                // byte -> byte offset sym*128 into this lane's column of the table
+                const uint32_t oa = sa == 0 ? ((w << 7) & 0x7f80u) : ((w >> (sa - 7)) & 0x7f80u);
+                const uint32_t ob = (w >> (sb - 7)) & 0x7f80u;
+                const uint2 ea = *reinterpret_cast<const uint2 *>(table_lane + oa);
+                const uint2 eb = *reinterpret_cast<const uint2 *>(table_lane + ob);
+                const uint32_t len = ea.y + eb.y;
+                longest = max(longest, len);
+                pair_len[j] = len;
+                pair_code[j] = __funnelshift_lc(0u, ea.x, eb.y) | eb.x;
+                my_bits += len;
             }
-            const uint32_t len = ea.y + eb.y;
-            slow |= len > 32u;
-            pair_len[j] = len;
-            pair_code[j] = __funnelshift_lc(0u, ea.x, eb.y) | eb.x;
-            my_bits += len;
+            slow = longest > 32u;
+        } else {  // ragged first or last tile: only the bit total is needed here, the per-symbol path below does the rest
+#pragma unroll
+            for (int j = 0; j < kPairs; ++j) pair_code[j] = pair_len[j] = 0;
+#pragma unroll 1
+            for (int i = 0; i < kPackItems; ++i) {
+                const uint32_t sym = (rw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                if ((valid >> i) & 1u) my_bits += reinterpret_cast<const uint2 *>(table_lane + sym * (kTableLanes * 8))->y;
+            }
         }
 
         // ---- (2) block scan of bit totals (and the sum of the earlier tiles of the group)
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
         }
         if (lane == 31) sh.warp_sum[warp] = incl;
         // B_i: first bit of the tile in the output
-        const unsigned long long bit_begin = a.group_prefix[tile / a.group_tiles] + a.tile_bits[tile];
+        const unsigned long long bit_begin = a.group_prefix[tile >> a.group_shift] + a.tile_bits[tile];
         const bool tile_slow = __syncthreads_or(slow);  // B1
         uint32_t warp_off = 0, tile_bits = 0;
 #pragma unroll
@@ -656,6 +666,10 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
     a.tile_bits = s.tile_bits;
     a.group_prefix = s.group_prefix;
     a.group_tiles = 1;
+    a.group_shift = 0;
+    a.interior_lo = g.misalign ? 1u : 0u;
+    a.interior_hi = (uint32_t)(g.v_end / kPackTileSyms);
+    if (a.interior_hi < a.interior_lo) a.interior_hi = a.interior_lo;
 
     if (wide) {
         // look-back descriptors and the ticket start from zero
@@ -677,6 +691,7 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         err = cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err != cudaSuccess) return err;
         a.group_tiles = pack_group_tiles(g.num_tiles);
+        for (a.group_shift = 0; (1u << a.group_shift) < a.group_tiles; ++a.group_shift) {}
         const uint32_t groups = (g.num_tiles + a.group_tiles - 1) / a.group_tiles;
         tile_bits_kernel<<<groups, kPackThreads, 0, stream>>>(a);
         group_scan_kernel<<<1, 1024, 0, stream>>>(a, groups);
