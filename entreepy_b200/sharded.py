@@ -148,6 +148,27 @@ class GpuBackend:
     def first_byte(self, t_buf):
         return int(t_buf[0].item())
 
+    def head_symbols(self, t_in, n):
+        """The first (up to 8) text bytes of the shard, as an int (little endian)."""
+        k = min(n, 8)
+        return int.from_bytes(bytes(t_in[:k].cpu().numpy()), "little") if k else 0
+
+
+def first_output_byte(cb, head, n, phase):
+    """First byte a shard writes when packed at bit `phase`: its leading codes behind `phase` zero bits.
+    None when the shard's first 8 symbols do not fill the byte (then the ranks exchange the real byte)."""
+    acc, nbits = 0, 0
+    for i in range(min(n, 8)):
+        c = cb.code[(head >> (8 * i)) & 0xFF]
+        length = int(c.length)
+        if length > 32:
+            return None
+        acc = (acc << length) | (int(c.data) & ((1 << length) - 1))
+        nbits += length
+        if nbits >= 8 - phase:
+            return (acc >> (nbits - (8 - phase))) & 0xFF
+    return None
+
 
 class ShardedCodec:
     def __init__(self, backend, plan, comm):
@@ -164,7 +185,10 @@ class ShardedCodec:
         cb = build_codebook(counts)                                 # same tables on every rank
         header = write_header(cb, p.n_total)
         bits = be.shard_bits(local, cb)
-        gathered = self.comm.allgather_ints([bits])                 # exchange 2: the cross-GPU scan of bit offsets
+        # exchange 2: the cross-GPU scan of bit offsets; the first text bytes of every shard ride along so
+        # that each rank can work out the seam byte of its right neighbours without a third exchange
+        head = be.head_symbols(t_in, p.n_local) if hasattr(be, "head_symbols") else 0
+        gathered = self.comm.allgather_ints([bits, head & 0x7FFFFFFFFFFFFFFF, head >> 63, p.n_local])
         offs = [0]
         for r in range(p.world):
             offs.append(offs[-1] + gathered[r][0])
@@ -172,14 +196,28 @@ class ShardedCodec:
         nbytes = be.pack_shard(t_in, p.n_local, cb, my_off & 7, bits, t_out)   # K2 at the final bit position
         res = EncodeResult(total_bytes=len(header) + (offs[-1] + 7) // 8, header=header, bit_offsets=offs,
                            first_byte=my_off >> 3, local_bytes=nbytes, codebook=cb)
-        # exchange 3: the byte in which rank r ends may also hold the first bits of the ranks after it
+        # the byte in which rank r ends may also hold the first bits of the ranks after it
         if p.world > 1:
-            firsts = self.comm.allgather_ints([be.first_byte(t_out) if nbytes else 0])
             last = (offs[p.rank + 1] - 1) >> 3 if bits else -1
+            sharers = [q for q in range(p.rank + 1, p.world)
+                       if offs[q + 1] > offs[q] and (offs[q] & 7) and (offs[q] >> 3) == last]
+            firsts = {}
+            for q in sharers:
+                hq = gathered[q][1] | (gathered[q][2] << 63)
+                firsts[q] = first_output_byte(cb, hq, gathered[q][3], offs[q] & 7) if hasattr(be, "head_symbols") else None
+            # every rank takes the same decision: the inputs are the gathered values
+            need_exchange = False
+            for q in range(1, p.world):
+                if offs[q + 1] > offs[q] and (offs[q] & 7):
+                    hq = gathered[q][1] | (gathered[q][2] << 63)
+                    if not hasattr(be, "head_symbols") or first_output_byte(cb, hq, gathered[q][3], offs[q] & 7) is None:
+                        need_exchange = True
+            if need_exchange:  # exchange 3 (tiny shards, dropped symbols): the real first bytes
+                got = self.comm.allgather_ints([be.first_byte(t_out) if nbytes else 0])
+                firsts = {q: got[q][0] for q in sharers}
             merged = 0
-            for q in range(p.rank + 1, p.world):
-                if offs[q + 1] > offs[q] and (offs[q] & 7) and (offs[q] >> 3) == last:
-                    merged |= firsts[q][0]
+            for q in sharers:
+                merged |= firsts[q]
             if merged:
                 be.or_byte(t_out, last - res.first_byte, merged)
         # bytes of the body that are final in this rank's buffer: a shard that starts inside a byte leaves
