@@ -20,7 +20,8 @@ struct et_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;       // context-owned stream (used when the caller passes none)
-    cudaStream_t copy_stream = nullptr;  // second stream for overlapped host copies
+    cudaStream_t copy_stream = nullptr;  // second stream for overlapped host copies (uploads)
+    cudaStream_t copy_stream2 = nullptr; // third stream: downloads, so that both directions of the link run at once
     cudaEvent_t ev[6] = {};
     // device scratch, grown on demand
     void *d_scratch = nullptr;
@@ -250,6 +251,7 @@ extern "C" int et_ctx_create(int device, et_ctx **out) {
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     ok = ok && cudaMalloc(reinterpret_cast<void **>(&ctx->d_small), kSmallBytes) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_small), kSmallBytes, cudaHostAllocDefault) == cudaSuccess;
@@ -274,6 +276,7 @@ extern "C" void et_ctx_destroy(et_ctx *ctx) {
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
     delete ctx;
 }
 
@@ -452,9 +455,8 @@ extern "C" int et_pack_shard_dev(et_ctx *ctx, const void *d_in, size_t n, const 
 // ====================================================================== decode
 namespace {
 
-// Decode a device-resident body.  *n_symbols = symbols the stream holds, capped at max_symbols.
-int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, uint8_t *d_out, uint64_t max_symbols,
-               uint64_t *n_symbols, cudaStream_t s, StageTimer *tm = nullptr, uint32_t *entry_exit = nullptr) {
+// Build the decoder tables for `dict` and queue their upload on `s`.
+int upload_unpack_tables(et_ctx *ctx, const et_dictionary &dict, cudaStream_t s) {
     UnpackTables *t = new (std::nothrow) UnpackTables;
     if (!t) return ET_ERR_OUT_OF_MEMORY;
     int rc = make_unpack_tables(dict, t);
@@ -468,6 +470,17 @@ int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, 
     const size_t tbl_bytes = sizeof t->clut + sizeof t->wlut + (size_t)t->n_nodes * 4;
     delete t;
     ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffLut, ctx->h_small + kOffLut, tbl_bytes, cudaMemcpyHostToDevice, s));
+    return ET_OK;
+}
+
+// Decode the part of a device-resident body that `g` describes.  *n_symbols = symbols found, capped at
+// max_symbols.  tables_ready: upload_unpack_tables() was already called for this dictionary (the
+// pipelined host path does it before it queues the bulk uploads, which would otherwise delay it).
+int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, uint8_t *d_out, uint64_t max_symbols,
+               uint64_t *n_symbols, cudaStream_t s, StageTimer *tm = nullptr, uint32_t *entry_exit = nullptr,
+               bool tables_ready = false) {
+    int rc = tables_ready ? ET_OK : upload_unpack_tables(ctx, dict, s);
+    if (rc != ET_OK) return rc;
     if (tm) tm->mark(2);
 
     const uint32_t chunk_bytes = unpack_chunk_bytes(g, ctx->num_sms);
@@ -555,15 +568,70 @@ extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
         if (rc != ET_OK) return rc;
         rc = ensure_bulk(ctx, &ctx->d_out, &ctx->d_out_cap, want + 16);
         if (rc != ET_OK) return rc;
-        if (body_bytes)
-            ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, in + dict.body_offset, body_bytes, cudaMemcpyHostToDevice, s));
-        rc = unpack_dev(ctx, unpack_geometry(ctx->d_in, body_bytes), dict, ctx->d_out, want, &produced, s);
-        if (rc != ET_OK) return rc;
-        if (write_out) {
-            if (produced == cap && dict.body_len > cap)
+        // D3, pipelined over the PCIe link: the body goes up in slices on one copy stream, each
+        // slice is decoded as soon as it (and 64 bytes of the next one) has landed, and its text
+        // goes back down on a second copy stream while the next slice is decoded — upload,
+        // decode and download overlap (the link is full duplex).  A slice starts on the exact
+        // codeword boundary at which the slice before it ended, so nothing is guessed.
+        const size_t kSlice = (size_t)64 << 20;
+        const size_t n_slices = body_bytes > 2 * kSlice ? (body_bytes + kSlice - 1) / kSlice : 1;
+        if (n_slices == 1) {
+            if (body_bytes)
+                ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, in + dict.body_offset, body_bytes, cudaMemcpyHostToDevice, s));
+            rc = unpack_dev(ctx, unpack_geometry(ctx->d_in, body_bytes), dict, ctx->d_out, want, &produced, s);
+            if (rc != ET_OK) return rc;
+            if (write_out) {
+                if (produced == cap && dict.body_len > cap)
+                    return fail(ctx, ET_ERR_NO_SPACE, "NoSpaceLeft: %u symbols, capacity %zu", dict.body_len, cap);
+                if (produced) ET_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, produced, cudaMemcpyDeviceToHost, s));
+                ET_CUDA(ctx, cudaStreamSynchronize(s));
+            }
+        } else {
+            rc = upload_unpack_tables(ctx, dict, s);  // before the bulk uploads: copies in one direction run in issue order
+            if (rc != ET_OK) return rc;
+            std::vector<cudaEvent_t> up(n_slices, nullptr);
+            auto cleanup = [&]() {
+                for (auto &e : up)
+                    if (e) cudaEventDestroy(e);
+            };
+            const uint8_t *body = in + dict.body_offset;
+            for (size_t k = 0; k < n_slices; ++k) {  // every upload is queued at once; events mark their arrival
+                const size_t lo = k * kSlice, hi = std::min(body_bytes, lo + kSlice);
+                cudaError_t e = cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_in + lo, body + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(up[k], ctx->copy_stream);
+                if (e != cudaSuccess) {
+                    cleanup();
+                    return fail(ctx, ET_ERR_CUDA, "upload of slice %zu: %s", k, cudaGetErrorString(e));
+                }
+            }
+            uint64_t head_bit = 0;  // first codeword of the next slice, bits from the start of the body
+            for (size_t k = 0; k < n_slices && produced < want; ++k) {
+                const bool last = k + 1 == n_slices;
+                // slice k owns body bytes [k*kSlice - 64, (k+1)*kSlice - 64): what it needs to look ahead is uploaded
+                const size_t own_lo = k ? k * kSlice - 64 : 0, own_hi = last ? body_bytes : (k + 1) * kSlice - 64;
+                const size_t avail = std::min(body_bytes, (k + 1) * kSlice);
+                cudaStreamWaitEvent(s, up[k], 0);
+                uint32_t ee[2] = {0, 0};
+                uint64_t got = 0;
+                rc = unpack_dev(ctx, unpack_geometry_shard(ctx->d_in, avail, own_lo, own_hi, (long long)head_bit), dict,
+                                ctx->d_out + produced, want - produced, &got, s, nullptr, ee, true);
+                if (rc != ET_OK) {
+                    cudaStreamSynchronize(ctx->copy_stream);
+                    cleanup();
+                    return rc;
+                }
+                head_bit = (uint64_t)own_hi * 8 + ee[1];
+                if (write_out && got)  // unpack_dev returned after its kernels finished: the text is ready to go down
+                    cudaMemcpyAsync(out + produced, ctx->d_out + produced, got, cudaMemcpyDeviceToHost, ctx->copy_stream2);
+                produced += got;
+            }
+            cudaStreamSynchronize(ctx->copy_stream);
+            const cudaError_t e = cudaStreamSynchronize(ctx->copy_stream2);
+            cleanup();
+            if (e != cudaSuccess) return fail(ctx, ET_ERR_CUDA, "download: %s", cudaGetErrorString(e));
+            if (write_out && produced == cap && dict.body_len > cap)
                 return fail(ctx, ET_ERR_NO_SPACE, "NoSpaceLeft: %u symbols, capacity %zu", dict.body_len, cap);
-            if (produced) ET_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, produced, cudaMemcpyDeviceToHost, s));
-            ET_CUDA(ctx, cudaStreamSynchronize(s));
         }
         if (print_out && produced) {  // decode.zig:189 prints every symbol to std_out
             std::vector<uint8_t> text(produced);

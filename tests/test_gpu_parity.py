@@ -208,3 +208,20 @@ def test_decode_every_length_up_to_two_chunks_and_all_alignments(codec):
         got = codec.decode_dev(dev.data_ptr() + phase + 4, len(et_file) - 4, out.data_ptr() + (phase * 7) % 16, data.size)
         o = (phase * 7) % 16
         assert got == data.size and out[o : o + got].cpu().numpy().tobytes() == data.tobytes(), phase
+
+
+def test_host_decode_pipelined_in_slices(codec, manifest):
+    # bodies above 128 MiB are uploaded, decoded and downloaded in overlapping 64 MiB slices (et_decode);
+    # every slice must start exactly where the one before it ended
+    import torch
+
+    thr = synth.thresholds_from_weights(synth.text_weights(manifest["midsummer_histogram"]))
+    n = (3 << 26) * 4 // 3 + 12345  # ~256 MiB of text -> ~150 MiB of body: three slices
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    codec.synth_dev(dev.data_ptr(), n, synth.SEED, 0, thr)
+    h_in, h_et, h_out = codec.pinned(n), codec.pinned(n + 16384), codec.pinned(n)
+    torch.from_numpy(h_in)[:] = dev.cpu()
+    size = codec.encode_into(h_in, h_et)
+    assert size - 400 > (128 << 20)
+    got = codec.decode_into(h_et[4:size], h_out)
+    assert got == n and np.array_equal(h_out, h_in)
