@@ -352,6 +352,14 @@ def run_ours(args, rank, world):
     # round trip == original (north_star): the text this rank decoded is text[offset : offset + got]
     if world == 1:
         verified = got == n and bool(torch.equal(arm.dec[:n], inp[:n]))
+        if not verified and kind == "uniform256":
+            # all 256 byte values occur: the reference encoder gives the last symbol in sort order no code
+            # (encode.zig:70), so the round trip is the text WITHOUT that symbol — by construction
+            counts = codec.histogram_dev(inp.data_ptr(), n)
+            cb = et.build_codebook(counts)
+            dropped = [s for s in range(256) if counts[s] and cb.code[s].length == 0]
+            keep = inp[:n][inp[:n] != dropped[0]] if len(dropped) == 1 else inp[:0]
+            verified = len(dropped) == 1 and got == keep.numel() and bool(torch.equal(arm.dec[:got], keep))
     else:
         want = torch.empty(got + 16, dtype=torch.uint8, device="cuda")
         if kind == "file":

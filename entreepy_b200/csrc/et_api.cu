@@ -483,7 +483,7 @@ int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, 
     if (rc != ET_OK) return rc;
     if (tm) tm->mark(2);
 
-    const uint32_t chunk_bytes = unpack_chunk_bytes(g, ctx->num_sms);
+    const uint32_t chunk_bytes = unpack_chunk_bytes(g, ctx->num_sms, dict.min_length, dict.max_length);
     rc = ensure_scratch(ctx, unpack_scratch_bytes(g, chunk_bytes));
     if (rc != ET_OK) return rc;
     const uint32_t *d_clut = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffLut);

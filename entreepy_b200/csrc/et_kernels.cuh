@@ -67,7 +67,7 @@ UnpackGeometry unpack_geometry_shard(const void *d_range, size_t range_bytes, si
 constexpr uint32_t kErrInvalidCode = 2u;
 
 // Chunk size for this stream (bytes per thread) and the device scratch the decoder needs.
-uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms);
+uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms, uint32_t min_length, uint32_t max_length);
 size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes);
 // Scratch header after the call: [4] error flags (u32), [8] symbols found (u64), [24] entry used
 // by the first chunk, [28] exit of the last chunk (u32 bits).  Writes min(total, max_symbols)

@@ -602,11 +602,17 @@ UnpackGeometry unpack_geometry_shard(const void *d_range, size_t range_bytes, si
     return g;
 }
 
-// Chunk size: 256 B unless the stream is so short that this would leave most of the GPU idle.
-uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms) {
+// Chunk size.  256 B suits codes that re-synchronise within a few symbols.  When all code
+// lengths are (nearly) equal a wrong parse survives for kilobytes (uniform bytes: 7/8-bit
+// codes, ~2 KB on average), and every fixpoint round repairs only one chunk's worth of it, so
+// such codes get chunks longer than their synchronisation distance.  Short streams get
+// shorter chunks so that the GPU is not left mostly idle.
+uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms, uint32_t min_length, uint32_t max_length) {
     const uint64_t bytes = (g.own_end_bit - g.own_begin_bit + 7) / 8;
-    uint32_t cb = 256;
-    while (cb > 32 && bytes / cb < (uint64_t)num_sms * 2048) cb >>= 1;
+    const uint32_t spread = max_length - min_length;
+    uint32_t cb = spread <= 1 ? 4096u : spread == 2 ? 1024u : 256u;
+    const uint32_t floor_cb = cb > 256u ? 256u : 32u;
+    while (cb > floor_cb && bytes / cb < (uint64_t)num_sms * 2048) cb >>= 1;
     return cb;
 }
 
@@ -665,6 +671,30 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     if (err != cudaSuccess) return err;
     if (launches) *launches += 2;
     uint32_t rounds = 2;
+    // Fixpoint rounds, four per host visit (the flag is cleared before the last of them: a round
+    // that changed nothing is the proof).
+    auto settle = [&]() -> cudaError_t {
+        for (;;) {
+            for (int i = 0; i < 3; ++i) chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, (int)rounds + i);
+            cudaError_t e = cudaMemsetAsync(a.changed, 0, 4, stream);
+            if (e != cudaSuccess) return e;
+            chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, (int)rounds + 3);
+            rounds += 4;
+            if (launches) *launches += 4;
+            e = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return e;
+            if (*h_flag == 0) return cudaSuccess;
+            if (rounds > n + 8u) return cudaErrorUnknown;  // cannot happen: each round settles one more chunk
+        }
+    };
+    // Long chunks were chosen because this code synchronises slowly: the guesses are known to be
+    // poor, so settle the entries before spending a write walk on them.
+    if (chunk_bytes > 256u) {
+        err = settle();
+        if (err != cudaSuccess) return err;
+    }
     for (;;) {
         chunk_sum_kernel<<<nb, kChunkThreads, 0, stream>>>(a);
         chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, nb);
@@ -675,21 +705,8 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
         err = cudaStreamSynchronize(stream);
         if (err != cudaSuccess) return err;
         if (*h_flag == 0) break;  // every entry was the true one: what the write walk produced stands
-        for (;;) {
-            // two check rounds per host visit: the second finds nothing to do once the first settled everything
-            chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, (int)rounds);
-            err = cudaMemsetAsync(a.changed, 0, 4, stream);
-            if (err != cudaSuccess) return err;
-            chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, (int)rounds + 1);
-            rounds += 2;
-            if (launches) *launches += 2;
-            err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream);
-            if (err != cudaSuccess) return err;
-            err = cudaStreamSynchronize(stream);
-            if (err != cudaSuccess) return err;
-            if (*h_flag == 0) break;
-            if (rounds > n + 4u) return cudaErrorUnknown;  // cannot happen: each round settles one more chunk
-        }
+        err = settle();
+        if (err != cudaSuccess) return err;
         // the error flags the first write walk may have raised came from a wrong parse
         err = cudaMemsetAsync(a.error_flags, 0, 4, stream);
         if (err != cudaSuccess) return err;
