@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
         const uint64_t pair0 = k.begin >> 8;
         const uint32_t n_pairs = a.chunk_bytes >> 5;
         const uint32_t wlut_s = smem_addr(wlut_sh);
-        prefetch_chunk_l2(a, k);
+        // (no L2 prefetch of the whole chunk here: with the text also streaming out, lines fetched that early are evicted before use)
         uint32_t w[5];
         const uint32_t n_pieces = a.chunk_bytes >> 4;
         (void)n_pairs;
