@@ -25,6 +25,9 @@
 // long contiguous run there is no per-subsequence speculation: two table walks per symbol
 // in total (count, write).  Anything unusual (ragged ends of the stream, output clipped by
 // body_len) takes the generic walker, one symbol at a time with every check.
+#include <cstdio>
+#include <cstdlib>
+
 #include "et_device.cuh"
 #include "et_kernels.cuh"
 
@@ -52,6 +55,8 @@ struct DecArgs {
     uint32_t *count;              // [n] symbols that begin inside the chunk
     unsigned long long *block_prefix;  // [ceil(n / kChunkThreads)] exclusive scan of per-block symbol counts
     uint32_t *changed;            // [1]
+    uint32_t *max_sum;            // [1] symbols of the largest region
+    unsigned long long *group_prefix;  // [ceil(regions / 1024)] lane-interleaved decoder: scan of the group sums
     uint32_t *error_flags;
     unsigned long long *total;
     uint32_t *entry_exit;
@@ -463,14 +468,15 @@ __global__ void __launch_bounds__(kChunkThreads) chunk_sum_kernel(const DecArgs 
     }
 }
 
-// One block: in-place exclusive scan of the block sums; total and the shard's entry/exit.
-__global__ void __launch_bounds__(1024) chunk_scan_kernel(const DecArgs a, uint32_t n_blocks) {
+// One block: in-place exclusive scan of `arr` (block sums, or the sums of groups of 1024 regions); total and the
+// shard's entry/exit.
+__global__ void __launch_bounds__(1024) chunk_scan_kernel(const DecArgs a, unsigned long long *arr, uint32_t n_blocks) {
     __shared__ unsigned long long part[1024];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (n_blocks + 1023u) / 1024u;
     const uint32_t lo = min(t * per, n_blocks), hi = min(lo + per, n_blocks);
     unsigned long long sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) sum += a.block_prefix[i];
+    for (uint32_t i = lo; i < hi; ++i) sum += arr[i];
     part[t] = sum;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {
@@ -481,8 +487,8 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const DecArgs a, uint3
     }
     unsigned long long run = part[t] - sum;
     for (uint32_t i = lo; i < hi; ++i) {
-        const unsigned long long v = a.block_prefix[i];
-        a.block_prefix[i] = run;
+        const unsigned long long v = arr[i];
+        arr[i] = run;
         run += v;
     }
     if (t == 1023) {
@@ -565,6 +571,495 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
     if (bad) atomicOr(a.error_flags, kErrInvalidCode);
 }
 
+// ====================================================================== lane-interleaved decoder
+// The fast path for long streams whose code re-synchronises quickly.  Same protocol as above
+// (run-up from a guess, repair rounds, fixpoint check, scan, write walk) but the unit of work
+// is a REGION: 32 consecutive chunks of 33 stream words, one warp per region, one lane per chunk.
+//   * the region (plus 16 bytes either side) is brought into shared memory by coalesced 16-byte
+//     loads and byte-swapped once on the way in.  A chunk is 33 words, so lane L reads image word
+//     33 L + j: bank (L + j) mod 32 — lanes at the same depth of their chunks never conflict;
+//   * the walk is ONE flat loop: two table lookups, then at most one 32-bit refill of a 64-bit
+//     window (a lookup consumes at most 12 bits, so two always fit).  The lanes of a warp meet
+//     again only at the end of the chunk, not at every stream word as the per-thread walkers
+//     above must (their words live in registers and cannot be indexed dynamically);
+//   * the write walk assembles the text of the whole region in shared memory at its final
+//     relative position (the chunks of a region are consecutive in the text as well), four
+//     symbols per shared store, and the warp copies it out as aligned 16-byte vectors: no
+//     partly written sector ever reaches L2 except at the two ends of a region.
+constexpr uint32_t kLaneWords = 33;
+constexpr uint32_t kLaneBytes = kLaneWords * 4;
+constexpr uint32_t kRegionBytes = 32 * kLaneBytes;            // 4224 = 33 lines of 128 bytes
+constexpr uint32_t kImgBytes = 16 + kRegionBytes + 16;        // run-up of lane 0 | region | look-ahead of lane 31
+constexpr uint32_t kRunupWords = 4;
+constexpr int kSyncWarps = 8;
+
+struct BitBuf {
+    uint32_t hi, lo, nxt;  // three consecutive stream words; the window is cut from hi:lo
+    uint32_t addr;         // shared address of the word after nxt
+};
+__device__ __forceinline__ void buf_open(BitBuf &b, uint32_t addr0) {
+    b.hi = lds_u32(addr0);
+    b.lo = lds_u32(addr0 + 4);
+    b.nxt = lds_u32(addr0 + 8);
+    b.addr = addr0 + 12;
+}
+__device__ __forceinline__ void buf_shift(BitBuf &b) {
+    b.hi = b.lo;
+    b.lo = b.nxt;
+    b.nxt = lds_u32(b.addr);
+    b.addr += 4;
+}
+// Top 32 bits of (hi:lo) << pos, pos < 64 (one funnel shift on the 64-bit pair).
+__device__ __forceinline__ uint32_t window64(const BitBuf &b, uint32_t pos) {
+    return (uint32_t)(((((uint64_t)b.hi << 32) | b.lo) << (pos & 63u)) >> 32);
+}
+// One code longer than the first-level window at bit pos (< 32) of hi:lo.  Returns its length, 0 = no such code.
+__device__ __forceinline__ uint32_t long_code_at(const BitBuf &b, uint32_t pos, const DecArgs &a, uint32_t *sym) {
+    const uint32_t win = __funnelshift_l(b.lo, b.hi, pos);
+    return long_code(win, __ldg(a.wlut + (win >> (32 - kLutBits))) & 0xffffu, a.nodes, sym);
+}
+
+// Count walk over `nwords` stream words whose first word is at shared address addr0, starting at
+// bit pos0 (< 32) of that word.  Consumes every symbol that begins before the end of the last
+// word.  Returns the symbol count; *exit_bits = bits past that end at which the walk stopped.
+// Walk state c: bits 0-6 position relative to b.hi (below 64 inside the main loop, up to 95 at the
+// very end), bits 9+ symbols.  Table entries (16 bit):
+// bits consumed | symbols << 9 for every whole code in the window, 0 = the first code is longer
+// than the window (the state does not move; the second lookup of a pair then reads 0 as well).
+__device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, uint32_t pos0, uint32_t clut_s,
+                                               const DecArgs &a, uint32_t *exit_bits) {
+    BitBuf b;
+    buf_open(b, addr0);
+    uint32_t c = pos0;
+    const uint32_t limit = addr0 + 4u * (nwords + 1u);  // b.addr == limit: hi:lo are the last two words
+    while (b.addr < limit) {
+        c += lds_u16(clut_s + ((window64(b, c) >> (31 - kLutBits)) & ((kLutSize - 1) << 1)));
+        const uint32_t e2 = lds_u16(clut_s + ((window64(b, c) >> (31 - kLutBits)) & ((kLutSize - 1) << 1)));
+        c += e2;
+        if (e2 == 0) {  // rare: a code of more than 12 bits
+            if (c & 32u) {
+                buf_shift(b);
+                c -= 32u;
+            }
+            uint32_t sym;
+            const uint32_t len = long_code_at(b, c & 31u, a, &sym);
+            c += len ? (len | (1u << 9)) : 1u;
+        }
+        if (c & 32u) {
+            buf_shift(b);
+            c -= 32u;
+        }
+    }
+    // the last words: hi:lo end 64 or 32 bits short of the chunk's end (32: a long code crossed a word at the very end)
+    uint32_t end_rel = 32u * (nwords + 3u) - 8u * (b.addr - addr0);
+    while ((c & 127u) + kLutBits <= end_rel) {  // whole windows that cannot cross the end
+        const uint32_t e = lds_u16(clut_s + ((window64(b, c) >> (31 - kLutBits)) & ((kLutSize - 1) << 1)));
+        if (e == 0) break;
+        c += e;
+    }
+    for (;;) {  // one symbol at a time up to the end
+        if ((c & 127u) >= end_rel) break;
+        if (c & 32u) {
+            buf_shift(b);
+            c -= 32u;
+            end_rel -= 32u;
+        }
+        const uint32_t win = __funnelshift_l(b.lo, b.hi, c & 31u);
+        uint32_t add = __ldg(a.clut + (win >> (32 - kLutBits))) >> 16;
+        if (add & kLutMarker) {
+            uint32_t sym;
+            const uint32_t len = long_code(win, __ldg(a.wlut + (win >> (32 - kLutBits))) & 0xffffu, a.nodes, &sym);
+            add = len ? (len | (1u << 9)) : 1u;
+        }
+        c += add;
+    }
+    *exit_bits = (c & 127u) - end_rel;
+    return c >> 9;
+}
+
+// Coalesced copy of a region's stream bytes (and 16 either side) into the warp's shared image,
+// big-endian words swapped to native.  Split in two so that the loads of the NEXT region can be
+// in flight (in registers) while the warp walks the current one.
+constexpr uint32_t kImgVecs = kImgBytes / 16;            // 266
+constexpr uint32_t kImgVecsPerLane = (kImgVecs + 31) / 32;  // 9
+struct RegionRegs {
+    uint4 v[kImgVecsPerLane];
+};
+__device__ __forceinline__ void region_load(const DecArgs &a, uint64_t region_byte, uint32_t lane, RegionRegs &q) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.body_aligned + region_byte - 16);
+#pragma unroll
+    for (uint32_t i = 0; i < kImgVecsPerLane; ++i)
+        if (i * 32 + lane < kImgVecs) q.v[i] = ld_stream_v4(src + i * 32 + lane);
+}
+__device__ __forceinline__ void region_store(const RegionRegs &q, uint32_t img_s, uint32_t lane) {
+#pragma unroll
+    for (uint32_t i = 0; i < kImgVecsPerLane; ++i)
+        if (i * 32 + lane < kImgVecs) {
+            const uint4 w = swap4(q.v[i]);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(img_s + (i * 32 + lane) * 16), "r"(w.x), "r"(w.y),
+                         "r"(w.z), "r"(w.w)
+                         : "memory");
+        }
+}
+__device__ __forceinline__ void region_prefetch_l2(const DecArgs &a, uint64_t region_byte, uint32_t lane) {
+    const uint8_t *p = a.body_aligned + region_byte + (uint64_t)lane * 128;  // 33 lines; the last one rides on lane 0's neighbour
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32 * 128));
+}
+
+struct Region {
+    uint64_t begin_byte;  // first byte of the region (16-byte aligned offset from body_aligned)
+    bool interior;        // the whole image is plain readable stream owned by this call, and it is not region 0
+};
+__device__ __forceinline__ Region region_of(const DecArgs &a, uint32_t r) {
+    Region g;
+    g.begin_byte = (a.grid_bit >> 3) + (uint64_t)r * kRegionBytes;
+    const uint64_t end_byte = g.begin_byte + kRegionBytes;
+    g.interior = r > 0 && end_byte * 8 <= a.own_end_bit && end_byte * 8 + 128 <= a.end_bit && end_byte + 16 <= a.byte_hi &&
+                 g.begin_byte >= a.byte_lo + 16;
+    return g;
+}
+
+// Count walk of a chunk that is not in an interior region (the ends of the stream): generic walker.
+__device__ __noinline__ void edge_count(const DecArgs &a, uint32_t gc, uint32_t start, bool known, uint32_t *entry,
+                                        uint32_t *cnt, uint32_t *exit_bits) {
+    const Chunk k = chunk_of(a, gc);
+    uint64_t pos = k.begin + start;
+    uint32_t bad = 0, dummy = 0;
+    if (!known && k.begin >= a.byte_lo * 8 + 128) {
+        pos = walk_generic<false>(a, k.begin - 128, k.begin, a.end_bit, &dummy, 0, &bad);
+        if (pos < k.begin) pos = k.begin;
+    }
+    *entry = (uint32_t)(pos - k.begin);
+    *cnt = 0;
+    if (pos < k.end) pos = walk_generic<false>(a, pos, k.end, a.end_bit, cnt, 0, &bad);
+    *exit_bits = pos > k.end ? (uint32_t)(pos - k.end) : 0u;
+}
+
+// Round 0 runs persistent (grid = resident CTAs, every warp strides over the regions, the table is
+// filled once per CTA); the repair rounds are launched one region per warp so that CTAs with
+// nothing to repair leave before they touch the table.
+__global__ void __launch_bounds__(kSyncWarps * 32, 5) region_sync_kernel(const DecArgs a, uint32_t n_regions, int round) {
+    __shared__ __align__(16) uint16_t clut_sh[kLutSize];
+    __shared__ __align__(16) uint8_t img[kSyncWarps][kImgBytes];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t stride = gridDim.x * kSyncWarps;
+    uint32_t r = blockIdx.x * kSyncWarps + warp;
+    if (round != 0) {  // one region per warp: is there anything to repair in this CTA?
+        const uint32_t gc = r * 32 + lane;
+        const bool work = gc > 0 && gc < a.n_chunks && a.exit_off[gc - 1] != a.start_off[gc];
+        if (!__syncthreads_or(work)) return;
+    }
+    for (int i = threadIdx.x; i < kLutSize; i += kSyncWarps * 32) {
+        const uint32_t e = a.clut[i] & 0xffffu;
+        clut_sh[i] = (e & kLutMarker) ? 0 : (uint16_t)e;
+    }
+    __syncthreads();
+    const uint32_t img_s = smem_addr(img[warp]), clut_s = smem_addr(clut_sh);
+    for (; r < n_regions; r += stride) {
+        const uint32_t gc = r * 32 + lane;
+        uint32_t start = 0;
+        bool work = gc < a.n_chunks;
+        if (work && round != 0) {
+            if (gc == 0) {
+                work = false;
+            } else {
+                start = a.exit_off[gc - 1];
+                work = start != a.start_off[gc];
+            }
+        }
+        if (!__any_sync(0xffffffffu, work)) continue;
+        if (work && round != 0) *a.changed = 1u;
+        if (gc == 0 && a.head_known) start = a.head_off;
+        const bool known = round != 0 || (gc == 0 && a.head_known);
+        const Region g = region_of(a, r);
+        uint32_t cnt = 0, entry = start, exit_bits = 0;
+        if (g.interior) {
+            RegionRegs q;
+            region_load(a, g.begin_byte, lane, q);
+            if (r + stride < n_regions) region_prefetch_l2(a, g.begin_byte + (uint64_t)stride * kRegionBytes, lane);
+            __syncwarp();  // the walk of the region before this one has left the image
+            region_store(q, img_s, lane);
+            __syncwarp();
+            if (work) {
+                const uint32_t chunk_s = img_s + 16 + lane * kLaneBytes;
+                if (!known) {
+                    uint32_t e;
+                    (void)lane_count(chunk_s - 4 * kRunupWords, kRunupWords, 0u, clut_s, a, &e);
+                    entry = e;
+                }
+                cnt = lane_count(chunk_s, kLaneWords, entry, clut_s, a, &exit_bits);
+            }
+        } else if (work) {
+            edge_count(a, gc, start, known, &entry, &cnt, &exit_bits);
+        }
+        if (work) {
+            a.start_off[gc] = (uint16_t)entry;
+            a.exit_off[gc] = (uint16_t)exit_bits;
+            a.count[gc] = cnt;
+        }
+    }
+}
+
+// Scan of the symbols per region, three small kernels: sums of every region and of every group
+// of 1024 regions (plus the largest region: it sizes the text stage of a warp); one-block scan of
+// the group sums (chunk_scan_kernel); scan inside every group.
+constexpr uint32_t kGroupRegions = 1024;
+__global__ void __launch_bounds__(1024) region_sum_kernel(const DecArgs a, uint32_t n_regions) {
+    __shared__ uint32_t warp_sum[32], warp_max[32];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t r0 = blockIdx.x * kGroupRegions + warp * 32;
+    uint32_t mine = 0;  // lane k keeps the sum of region r0 + k
+    for (uint32_t k = 0; k < 32; ++k) {
+        const uint32_t gc = (r0 + k) * 32 + lane;
+        uint32_t v = (r0 + k < n_regions && gc < a.n_chunks) ? a.count[gc] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == k) mine = v;
+    }
+    if (r0 + lane < n_regions) a.block_prefix[r0 + lane] = mine;
+    uint32_t sum = mine, big = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        big = max(big, __shfl_xor_sync(0xffffffffu, big, o));
+    }
+    if (lane == 0) {
+        warp_sum[warp] = sum;
+        warp_max[warp] = big;
+    }
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long s = 0;
+        uint32_t m = 0;
+        for (int i = 0; i < 32; ++i) {
+            s += warp_sum[i];
+            m = max(m, warp_max[i]);
+        }
+        a.group_prefix[blockIdx.x] = s;
+        atomicMax(a.max_sum, m);
+    }
+}
+__global__ void __launch_bounds__(1024) region_apply_kernel(const DecArgs a, uint32_t n_regions) {
+    __shared__ uint32_t warp_sum[32];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t r = blockIdx.x * kGroupRegions + t;
+    const uint32_t v = r < n_regions ? (uint32_t)a.block_prefix[r] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
+    if (r < n_regions) a.block_prefix[r] = a.group_prefix[blockIdx.x] + before + (incl - v);
+}
+
+// ------------------------------------------------------------------ write walk of a lane
+struct OutAcc {
+    uint32_t lo, hi;  // the last 8 symbols, newest in the top byte of hi
+    uint32_t A;       // shared address of the next text byte
+};
+// Append the `sh`/8 symbols in the low bytes of `syms` (sh = 0, 8 or 16).  When the text address
+// crosses a multiple of 4 the finished word is stored (one symbol of the next word may already
+// sit on top of it).  A lane's first word may hold bytes of the lane before it: those are
+// rewritten by that lane's lane_flush() after the warp has met.
+__device__ __forceinline__ void emit(OutAcc &r, uint32_t syms, uint32_t sh) {
+    r.lo = __funnelshift_r(r.lo, r.hi, sh);
+    r.hi = __funnelshift_r(r.hi, syms, sh);
+    const uint32_t a2 = r.A + (sh >> 3);
+    if ((r.A ^ a2) & 4u) sts_u32((a2 & ~3u) - 4u, __funnelshift_l(r.lo, r.hi, a2 << 3));
+    r.A = a2;
+}
+// The bytes after the lane's last whole word (at most 3, never before a_begin), one at a time.
+__device__ __forceinline__ void lane_flush(const OutAcc &r, uint32_t a_begin) {
+    uint32_t k = r.A & 3u;
+    if (r.A - a_begin < k) k = r.A - a_begin;
+    for (uint32_t i = 0; i < k; ++i) {
+        const uint32_t byte = (r.hi >> (8u * (4u - k + i))) & 0xffu;
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(r.A - k + i), "r"(byte) : "memory");
+    }
+}
+
+// Table entries of the write walk (32 bit): symbols (one or two) in bits 0-15, bits consumed in
+// 16-21, 8 x symbols in 27-31; 0 = the first code is longer than the window.
+__device__ __forceinline__ void lane_write(uint32_t addr0, uint32_t nwords, uint32_t pos0, uint32_t wlut_s, const DecArgs &a,
+                                           OutAcc &r, uint32_t *bad) {
+    BitBuf b;
+    buf_open(b, addr0);
+    uint32_t c = pos0;  // only bits 0-5 mean anything
+    const uint32_t limit = addr0 + 4u * (nwords + 1u);
+    while (b.addr < limit) {
+        const uint32_t e1 = lds_u32(wlut_s + ((window64(b, c) >> (30 - kLutBits)) & ((kLutSize - 1) << 2)));
+        c += e1 >> 16;
+        emit(r, e1, e1 >> 27);
+        const uint32_t e2 = lds_u32(wlut_s + ((window64(b, c) >> (30 - kLutBits)) & ((kLutSize - 1) << 2)));
+        c += e2 >> 16;
+        emit(r, e2, e2 >> 27);
+        if (e2 == 0) {
+            if (c & 32u) {
+                buf_shift(b);
+                c -= 32u;
+            }
+            uint32_t sym = 0;
+            const uint32_t len = long_code_at(b, c & 31u, a, &sym);
+            if (len) {
+                c += len;
+                emit(r, sym, 8u);
+            } else {
+                *bad = 1u;
+                c += 1u;
+            }
+        }
+        if (c & 32u) {
+            buf_shift(b);
+            c -= 32u;
+        }
+    }
+    uint32_t end_rel = 32u * (nwords + 3u) - 8u * (b.addr - addr0);
+    while ((c & 127u) + kLutBits <= end_rel) {
+        const uint32_t e = lds_u32(wlut_s + ((window64(b, c) >> (30 - kLutBits)) & ((kLutSize - 1) << 2)));
+        if (e == 0) break;
+        c += e >> 16;
+        emit(r, e, e >> 27);
+    }
+    for (;;) {
+        if ((c & 127u) >= end_rel) break;
+        if (c & 32u) {
+            buf_shift(b);
+            c -= 32u;
+            end_rel -= 32u;
+        }
+        const uint32_t win = __funnelshift_l(b.lo, b.hi, c & 31u);
+        const uint32_t idx = win >> (32 - kLutBits);
+        const uint32_t add = __ldg(a.clut + idx) >> 16;
+        uint32_t sym = lds_u32(wlut_s + idx * 4u) & 0xffu, len = add & 0xffu;
+        if (add & kLutMarker) {
+            len = long_code(win, __ldg(a.wlut + idx) & 0xffffu, a.nodes, &sym);
+            if (len == 0) {
+                *bad = 1u;
+                c += 1u;
+                continue;
+            }
+        }
+        c += len;
+        emit(r, sym, 8u);
+    }
+}
+
+// What the write walk of a region needs to know about it (loaded one region ahead).
+struct RegionMeta {
+    uint32_t cnt, start, prev_exit;
+    unsigned long long o_w;
+    bool live;
+};
+__device__ __forceinline__ RegionMeta region_meta(const DecArgs &a, uint32_t r, uint32_t lane) {
+    RegionMeta m;
+    const uint32_t gc = r * 32 + lane;
+    m.live = gc < a.n_chunks;
+    m.cnt = m.live ? a.count[gc] : 0u;
+    m.start = m.live ? a.start_off[gc] : 0u;
+    m.prev_exit = (m.live && gc > 0) ? a.exit_off[gc - 1] : m.start;
+    m.o_w = a.block_prefix[r];
+    return m;
+}
+
+// Dynamic shared memory: write table (16 KiB) | per warp: stream image (kImgBytes) + text stage (stage_bytes).
+// Persistent: one CTA per SM, every warp strides over the regions; the stream bytes and the
+// metadata of a warp's next region are requested before it walks the current one.
+__global__ void __launch_bounds__(512, 1) region_write_kernel(const DecArgs a, uint32_t n_regions, uint32_t stage_bytes) {
+    extern __shared__ __align__(16) uint8_t dyn[];
+    uint32_t *wlut_sh = reinterpret_cast<uint32_t *>(dyn);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kLutSize; i += blockDim.x) {
+        const uint32_t e = a.wlut[i], add = e >> 16;
+        wlut_sh[i] = (add & kLutMarker) ? 0u : ((e & 0xffffu) | ((add & 0xffu) << 16) | ((add >> 9) << 30));
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t stride = gridDim.x * (blockDim.x >> 5);
+    uint32_t r = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= n_regions) return;
+    const uint32_t img_s = smem_addr(dyn) + kLutSize * 4u + warp * (kImgBytes + stage_bytes);
+    const uint32_t stage_s = img_s + kImgBytes, wlut_s = smem_addr(wlut_sh);
+    uint32_t bad = 0;
+
+    RegionMeta m = region_meta(a, r, lane);
+    Region g = region_of(a, r);
+    RegionRegs q;
+    if (g.interior) region_load(a, g.begin_byte, lane, q);
+    for (;;) {
+        const uint32_t gc = r * 32 + lane;
+        const bool interior = g.interior;
+        if (interior) {
+            __syncwarp();  // the copy-out of the region before this one is done with the shared buffers
+            region_store(q, img_s, lane);
+        }
+        // request the next region
+        const uint32_t r_next = r + stride;
+        const RegionMeta m_cur = m;
+        if (r_next < n_regions) {
+            m = region_meta(a, r_next, lane);
+            g = region_of(a, r_next);
+            if (g.interior) region_load(a, g.begin_byte, lane, q);
+        }
+        // does every chunk start where its left neighbour ended?  (the fixpoint check rides along)
+        if (m_cur.live && gc > 0 && m_cur.prev_exit != m_cur.start) *a.changed = 1u;
+        const uint32_t cnt = m_cur.cnt;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += up;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned long long o_w = m_cur.o_w;
+        if (total != 0 && o_w < a.max_symbols) {
+            const unsigned long long o = o_w + (incl - cnt);
+            const unsigned long long o_end = o_w + total < a.max_symbols ? o_w + total : a.max_symbols;
+            uint8_t *dst_w = a.out + o_w;
+            const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(dst_w) & 15u);  // text of other regions in the first vector
+            if (interior && skew + total <= stage_bytes) {
+                __syncwarp();
+                OutAcc acc;
+                acc.lo = acc.hi = 0;
+                const uint32_t a_begin = stage_s + skew + (incl - cnt);
+                acc.A = a_begin;
+                if (cnt) lane_write(img_s + 16 + lane * kLaneBytes, kLaneWords, m_cur.start, wlut_s, a, acc, &bad);
+                __syncwarp();
+                if (cnt) lane_flush(acc, a_begin);
+                __syncwarp();
+                // the stage is an image of the text from the 16-byte boundary below dst_w: whole vectors leave as such
+                uint8_t *base = dst_w - skew;
+                const uint32_t first = skew, last = skew + (uint32_t)(o_end - o_w);
+                const uint32_t n_vec = (last + 15u) >> 4;
+                for (uint32_t v = lane; v < n_vec; v += 32) {
+                    const uint32_t b0 = v * 16u;
+                    if (b0 >= first && b0 + 16u <= last) {
+                        uint4 w;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                                     : "r"(stage_s + b0));
+                        st_stream_v4(base + b0, w);
+                    } else {
+                        const uint32_t lo = b0 > first ? b0 : first, hi = b0 + 16u < last ? b0 + 16u : last;
+                        for (uint32_t k = lo; k < hi; ++k) base[k] = (uint8_t)lds_u8(stage_s + k);
+                    }
+                }
+            } else if (m_cur.live && cnt) {  // the ends of the stream, or a region whose text does not fit the stage
+                const Chunk k = chunk_of(a, gc);
+                uint32_t n = 0;
+                if (k.begin + m_cur.start < k.end) walk_generic<true>(a, k.begin + m_cur.start, k.end, a.end_bit, &n, o, &bad);
+            }
+        }
+        if (r_next >= n_regions) break;
+        r = r_next;
+    }
+    if (bad) atomicOr(a.error_flags, kErrInvalidCode);
+}
+
 uint64_t chunk_count(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t grid_bit = g.own_begin_bit / 256 * 256;
     const uint64_t bits = (uint64_t)chunk_bytes * 8;
@@ -602,6 +1097,15 @@ UnpackGeometry unpack_geometry_shard(const void *d_range, size_t range_bytes, si
     return g;
 }
 
+// Streams of at least this many bytes take the lane-interleaved decoder (enough regions to give every
+// SM a full set of warps).  ET_LANE_MIN_BYTES overrides it (tests run the path on small inputs).
+static uint64_t lane_path_min_bytes(int num_sms) {
+    const char *v = getenv("ET_LANE_MIN_BYTES");
+    const long long env = v ? atoll(v) : -1ll;
+    if (env >= 0) return (uint64_t)env > 2 * kRegionBytes ? (uint64_t)env : 2 * kRegionBytes;
+    return (uint64_t)num_sms * 8 * kRegionBytes;
+}
+
 // Chunk size.  256 B suits codes that re-synchronise within a few symbols.  When all code
 // lengths are (nearly) equal a wrong parse survives for kilobytes (uniform bytes: 7/8-bit
 // codes, ~2 KB on average), and every fixpoint round repairs only one chunk's worth of it, so
@@ -610,6 +1114,7 @@ UnpackGeometry unpack_geometry_shard(const void *d_range, size_t range_bytes, si
 uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms, uint32_t min_length, uint32_t max_length) {
     const uint64_t bytes = (g.own_end_bit - g.own_begin_bit + 7) / 8;
     const uint32_t spread = max_length - min_length;
+    if (spread > 2 && bytes >= lane_path_min_bytes(num_sms)) return kLaneBytes;  // lane-interleaved decoder
     uint32_t cb = spread <= 1 ? 4096u : spread == 2 ? 1024u : 256u;
     const uint32_t floor_cb = cb > 256u ? 256u : 32u;
     while (cb > floor_cb && bytes / cb < (uint64_t)num_sms * 2048) cb >>= 1;
@@ -618,8 +1123,76 @@ uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms, uint32_t min_l
 
 size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t n = chunk_count(g, chunk_bytes);
-    const uint64_t nb = (n + kChunkThreads - 1) / kChunkThreads;
-    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2) + 64;
+    const uint64_t per = chunk_bytes == kLaneBytes ? 32 : kChunkThreads;  // chunks per scanned sum
+    const uint64_t nb = (n + per - 1) / per;
+    const uint64_t ng = (nb + kGroupRegions - 1) / kGroupRegions;
+    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2) + 64 + (size_t)ng * 8 + 64;
+}
+
+// Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
+// look at the scratch header after the scan: the largest region sizes the text stage of a warp.
+static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uint32_t *h_flag, cudaStream_t stream,
+                                       int *launches, uint32_t *rounds_out) {
+    static int max_smem = 0, num_sms = 0;
+    cudaError_t err;
+    if (!max_smem) {
+        int dev = 0;
+        if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+        if ((err = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+        if ((err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
+        if ((err = cudaFuncSetAttribute(region_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess)
+            return err;
+    }
+    const uint32_t sync_blocks = (n_regions + kSyncWarps - 1) / kSyncWarps;
+    const uint32_t resident = (uint32_t)num_sms * 5u;  // __launch_bounds__(.., 5)
+    region_sync_kernel<<<sync_blocks < resident ? sync_blocks : resident, kSyncWarps * 32, 0, stream>>>(a, n_regions, 0);
+    region_sync_kernel<<<sync_blocks, kSyncWarps * 32, 0, stream>>>(a, n_regions, 1);
+    if ((err = cudaMemsetAsync(a.changed, 0, 4, stream)) != cudaSuccess) return err;
+    if (launches) *launches += 2;
+    uint32_t rounds = 2;
+    for (;;) {
+        const uint32_t n_groups = (n_regions + kGroupRegions - 1) / kGroupRegions;
+        if ((err = cudaMemsetAsync(a.max_sum, 0, 4, stream)) != cudaSuccess) return err;
+        region_sum_kernel<<<n_groups, 1024, 0, stream>>>(a, n_regions);
+        chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, a.group_prefix, n_groups);
+        region_apply_kernel<<<n_groups, 1024, 0, stream>>>(a, n_regions);
+        if ((err = cudaMemcpyAsync(h_flag, a.max_sum, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
+        if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
+        // text stage of a warp: the largest region, 15 bytes of skew, whole vectors; as many warps as fit one SM
+        const uint32_t avail = (uint32_t)max_smem - kLutSize * 4u;
+        uint32_t stage = (*h_flag + 15u + 15u) & ~15u;
+        if (stage + kImgBytes > avail) stage = (avail - kImgBytes) & ~15u;  // regions that do not fit take the generic walker
+        uint32_t warps = avail / (stage + kImgBytes);
+        if (warps > 16u) warps = 16u;
+        const uint32_t smem = kLutSize * 4u + warps * (stage + kImgBytes);
+        if (getenv("ET_DEBUG_LANES"))
+            fprintf(stderr, "[lanes] regions=%u chunks=%u max_sum=%u stage=%u warps=%u smem=%u rounds=%u\n", n_regions, a.n_chunks,
+                    *h_flag, stage, warps, smem, rounds);
+        const uint32_t write_blocks = (n_regions + warps - 1) / warps;
+        region_write_kernel<<<write_blocks < (uint32_t)num_sms ? write_blocks : (uint32_t)num_sms, warps * 32, smem, stream>>>(
+            a, n_regions, stage);
+        if (launches) *launches += 4;
+        if ((err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
+        if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
+        if (getenv("ET_DEBUG_LANES")) fprintf(stderr, "[lanes] after write: changed=%u\n", *h_flag);
+        if (*h_flag == 0) break;  // every entry was the true one: what the write walk produced stands
+        // entries still moving: fixpoint rounds, four per host visit (the flag is cleared before the last of them)
+        for (;;) {
+            for (int i = 0; i < 3; ++i) region_sync_kernel<<<sync_blocks, kSyncWarps * 32, 0, stream>>>(a, n_regions, (int)rounds + i);
+            if ((err = cudaMemsetAsync(a.changed, 0, 4, stream)) != cudaSuccess) return err;
+            region_sync_kernel<<<sync_blocks, kSyncWarps * 32, 0, stream>>>(a, n_regions, (int)rounds + 3);
+            rounds += 4;
+            if (launches) *launches += 4;
+            if ((err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
+            if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
+            if (getenv("ET_DEBUG_LANES")) fprintf(stderr, "[lanes] repair rounds=%u changed=%u\n", rounds, *h_flag);
+            if (*h_flag == 0) break;
+            if (rounds > a.n_chunks + 8u) return cudaErrorUnknown;  // cannot happen: each round settles one more chunk
+        }
+        if ((err = cudaMemsetAsync(a.error_flags, 0, 4, stream)) != cudaSuccess) return err;  // raised by a wrong parse
+    }
+    if (rounds_out) *rounds_out = rounds;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
@@ -632,7 +1205,8 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     if (rounds_out) *rounds_out = 0;
     if (n64 == 0) return cudaSuccess;
     const uint32_t n = (uint32_t)n64;
-    const uint32_t nb = (n + kChunkThreads - 1) / kChunkThreads;
+    const bool lanes = chunk_bytes == kLaneBytes;
+    const uint32_t nb = lanes ? (n + 31u) / 32u : (n + kChunkThreads - 1) / kChunkThreads;
     DecArgs a;
     a.body_aligned = g.body_aligned;
     a.grid_bit = g.own_begin_bit / 256 * 256;  // chunks are whole 32-byte sectors
@@ -651,13 +1225,17 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.error_flags = reinterpret_cast<uint32_t *>(p + 4);
     a.total = reinterpret_cast<unsigned long long *>(p + 8);
     a.changed = reinterpret_cast<uint32_t *>(p + 16);
+    a.max_sum = reinterpret_cast<uint32_t *>(p + 20);
     a.entry_exit = reinterpret_cast<uint32_t *>(p + 24);
     a.block_prefix = reinterpret_cast<unsigned long long *>(p + 64);
     a.count = reinterpret_cast<uint32_t *>(p + 64 + (size_t)nb * 8);
     a.start_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 4);
     a.exit_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 6);
+    a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 8 + 63) & ~(size_t)63));
     a.out = d_out;
     a.max_symbols = max_symbols;
+
+    if (lanes) return launch_unpack_lanes(a, nb, h_flag, stream, launches, rounds_out);
 
     // Common case (codes that re-synchronise quickly): one walk from the guesses, one repair
     // round for the few chunks whose run-up was too short (text: 0.1 % of them; their exits do
@@ -697,7 +1275,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     }
     for (;;) {
         chunk_sum_kernel<<<nb, kChunkThreads, 0, stream>>>(a);
-        chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, nb);
+        chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, a.block_prefix, nb);
         chunk_write_kernel<<<nb, kChunkThreads, 0, stream>>>(a);
         if (launches) *launches += 3;
         err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream);
