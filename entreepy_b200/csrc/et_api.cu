@@ -45,7 +45,8 @@ constexpr size_t kOffCounts = 0;                                    // 256 x u64
 constexpr size_t kOffPackTables = 2048;                             // narrow 2 KiB | wide 2304 B
 constexpr size_t kOffLut = 8192;                                    // clut | wlut: 2 x 4096 x u32
 constexpr size_t kOffNodes = kOffLut + 2 * kLutSize * 4;            // kMaxTrieNodes x u32
-constexpr size_t kOffThresholds = kOffNodes + kMaxTrieNodes * 4;    // 256 x u32
+constexpr size_t kOffSlots = kOffNodes + kMaxTrieNodes * 4;         // kLutSize x u16 slot of a marker window | sub-tables
+constexpr size_t kOffThresholds = kOffSlots + kLutSize * 2 + (kMaxSubTables << kSubBits) * 2;  // 256 x u32
 constexpr size_t kOffFlags = kOffThresholds + 1024;                 // error flags + total (16 B)
 constexpr size_t kOffHeader = kOffFlags + 64;                       // 4 KiB header staging
 constexpr size_t kSmallBytes = kOffHeader + 4096;
@@ -467,9 +468,12 @@ int upload_unpack_tables(et_ctx *ctx, const et_dictionary &dict, cudaStream_t s)
     std::memcpy(ctx->h_small + kOffLut, t->clut, sizeof t->clut);
     std::memcpy(ctx->h_small + kOffLut + sizeof t->clut, t->wlut, sizeof t->wlut);
     std::memcpy(ctx->h_small + kOffNodes, t->nodes, (size_t)t->n_nodes * 4);
+    std::memcpy(ctx->h_small + kOffSlots, t->slot_of, sizeof t->slot_of);
+    std::memcpy(ctx->h_small + kOffSlots + sizeof t->slot_of, t->sub, sizeof t->sub);
     const size_t tbl_bytes = sizeof t->clut + sizeof t->wlut + (size_t)t->n_nodes * 4;
     delete t;
     ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffLut, ctx->h_small + kOffLut, tbl_bytes, cudaMemcpyHostToDevice, s));
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffSlots, ctx->h_small + kOffSlots, kOffThresholds - kOffSlots, cudaMemcpyHostToDevice, s));
     return ET_OK;
 }
 
@@ -491,7 +495,8 @@ int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, 
     const uint32_t *d_nodes = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffNodes);
     int launches = 0;
     uint32_t rounds = 0;
-    ET_CUDA(ctx, launch_unpack(g, chunk_bytes, d_clut, d_wlut, d_nodes, d_out, max_symbols, ctx->d_scratch,
+    const uint16_t *d_slots = reinterpret_cast<const uint16_t *>(ctx->d_small + kOffSlots);
+    ET_CUDA(ctx, launch_unpack(g, chunk_bytes, d_clut, d_wlut, d_nodes, d_slots, d_out, max_symbols, ctx->d_scratch,
                                reinterpret_cast<uint32_t *>(ctx->h_small + kOffFlags + 32), s, &launches, &rounds));
     ctx->launches += (uint64_t)launches;
     ctx->last_decode_rounds = rounds;

@@ -288,9 +288,28 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
             ++cnt;
             if (pos >= (unsigned)kLutBits) break;
         }
+        t->slot_of[idx] = kNoSlot;
         if (cnt == 0) {
             t->clut[idx] = kLutMarker | (kLutMarker << 16);
             t->wlut[idx] = (stuck_node & 0xFFFFu) | (kLutMarker << 16);
+            if (stuck_node != kChildNone && t->n_slots < kMaxSubTables) {  // second level: the next 8 bits
+                const uint32_t slot = t->n_slots++;
+                t->slot_of[idx] = (uint16_t)slot;
+                for (uint32_t nxt = 0; nxt < (1u << kSubBits); ++nxt) {
+                    uint32_t node = stuck_node;
+                    uint16_t e = 0;
+                    for (uint32_t k = 0; k < kSubBits; ++k) {
+                        const uint32_t c = kid[node][(nxt >> (kSubBits - 1 - k)) & 1u];
+                        if (c == kChildNone) break;
+                        if (c & kChildLeaf) {
+                            e = (uint16_t)((c & 0xFFu) | ((kLutBits + k + 1) << 8));
+                            break;
+                        }
+                        node = c;
+                    }
+                    t->sub[(slot << kSubBits) + nxt] = e;
+                }
+            }
         } else {
             const uint32_t all = pos | (cnt << 9), one = len0 | (1u << 9);
             const uint32_t two = cnt >= 2 ? (len01 | (2u << 9)) : one;

@@ -43,10 +43,21 @@ constexpr uint32_t kMaxTrieNodes = 8192;
 constexpr uint32_t kChildLeaf = 0x8000u;
 constexpr uint32_t kChildNone = 0xFFFFu;
 
+// Third table (lane-interleaved decoder): codes of kLutBits+1 .. kLutBits+8 bits without a trie walk.
+// Every first-level window that is a proper prefix of longer codes ("marker" entry) gets a slot;
+// sub[slot][next 8 bits] = symbol | length << 8, 0 = longer than that or no code.  Dictionaries with
+// more than kMaxSubTables such windows keep the trie for the rest.
+constexpr uint32_t kSubBits = 8;
+constexpr uint32_t kMaxSubTables = 16;
+constexpr uint16_t kNoSlot = 0xFFFFu;
+
 struct UnpackTables {
     uint32_t clut[kLutSize];
     uint32_t wlut[kLutSize];
     uint32_t nodes[kMaxTrieNodes];
+    uint16_t slot_of[kLutSize];                      // marker window -> slot, kNoSlot otherwise
+    uint16_t sub[kMaxSubTables << kSubBits];
+    uint32_t n_slots;
     uint32_t n_nodes;
     uint32_t max_length;
     uint32_t min_length;

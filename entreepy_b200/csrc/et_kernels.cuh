@@ -72,9 +72,10 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes);
 // Scratch header after the call: [4] error flags (u32), [8] symbols found (u64), [24] entry used
 // by the first chunk, [28] exit of the last chunk (u32 bits).  Writes min(total, max_symbols)
 // bytes to d_out.  Blocks on the stream between check rounds (h_flag: pinned host word).
+// d_slots: UnpackTables::slot_of followed by UnpackTables::sub (second-level tables of the lane-interleaved decoder).
 // *rounds_out = passes over the chunk entries it took (2 = the guesses plus one repair round sufficed).
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
-                          const uint32_t *d_nodes, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
+                          const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
                           uint32_t *h_flag, cudaStream_t stream, int *launches, uint32_t *rounds_out);
 
 // ---------------------------------------------------------------- synthetic input generator

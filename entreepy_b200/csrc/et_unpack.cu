@@ -50,9 +50,11 @@ struct DecArgs {
     const uint32_t *clut;
     const uint32_t *wlut;
     const uint32_t *nodes;
+    const uint16_t *slots;        // slot of every marker window (kLutSize), then the second-level tables
     uint16_t *start_off;          // [n] first codeword of the chunk, bits past the chunk's first bit
     uint16_t *exit_off;           // [n] first codeword boundary at or after the chunk's end, bits past that end
     uint32_t *count;              // [n] symbols that begin inside the chunk
+    uint32_t *mid;                // [n] lane-interleaved decoder: entry of the chunk's second part | symbols of the first << 16
     unsigned long long *block_prefix;  // [ceil(n / kChunkThreads)] exclusive scan of per-block symbol counts
     uint32_t *changed;            // [1]
     uint32_t *max_sum;            // [1] symbols of the largest region
@@ -66,6 +68,11 @@ struct DecArgs {
 
 // ------------------------------------------------------------------ shared-window accessors
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Makes a value opaque to the compiler, which otherwise recomputes shared-window addresses inside the hot loops.
+__device__ __forceinline__ uint32_t pinned(uint32_t x) {
+    asm volatile("" : "+r"(x));
+    return x;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -588,10 +595,14 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
 //     partly written sector ever reaches L2 except at the two ends of a region.
 constexpr uint32_t kLaneWords = 33;
 constexpr uint32_t kLaneBytes = kLaneWords * 4;
+constexpr uint32_t kSplitWords = 17;  // the write walk decodes words [0, 17) and [17, 33) of a chunk side by side
 constexpr uint32_t kRegionBytes = 32 * kLaneBytes;            // 4224 = 33 lines of 128 bytes
 constexpr uint32_t kImgBytes = 16 + kRegionBytes + 16;        // run-up of lane 0 | region | look-ahead of lane 31
 constexpr uint32_t kRunupWords = 4;
-constexpr int kSyncWarps = 8;
+constexpr int kSyncWarps = 16;
+constexpr uint32_t kSubBytes = (kMaxSubTables << kSubBits) * 2;   // second-level tables in shared memory
+constexpr uint32_t kTableBytes = kLutSize * 4 + kSubBytes;
+constexpr uint32_t kSyncSmem = kTableBytes + kSyncWarps * kImgBytes;
 
 struct BitBuf {
     uint32_t hi, lo, nxt;  // three consecutive stream words; the window is cut from hi:lo
@@ -613,28 +624,44 @@ __device__ __forceinline__ void buf_shift(BitBuf &b) {
 __device__ __forceinline__ uint32_t window64(const BitBuf &b, uint32_t pos) {
     return (uint32_t)(((((uint64_t)b.hi << 32) | b.lo) << (pos & 63u)) >> 32);
 }
-// One code longer than the first-level window at bit pos (< 32) of hi:lo.  Returns its length, 0 = no such code.
-__device__ __forceinline__ uint32_t long_code_at(const BitBuf &b, uint32_t pos, const DecArgs &a, uint32_t *sym) {
+// One code longer than the first-level window at bit pos (< 32) of hi:lo.  slot_e: the marker's
+// second-level slot (0x8000 | slot) or kNoSlot; sub_s: shared address of the second-level tables.
+// Returns the code's length, 0 = no such code.
+__device__ __forceinline__ uint32_t long_code_at(const BitBuf &b, uint32_t pos, uint32_t slot_e, uint32_t sub_s,
+                                                 const DecArgs &a, uint32_t *sym) {
     const uint32_t win = __funnelshift_l(b.lo, b.hi, pos);
+    if (slot_e != kNoSlot) {
+        const uint32_t se = lds_u16(sub_s + ((slot_e & (kMaxSubTables - 1)) << (kSubBits + 1)) +
+                                    ((win >> (31 - kLutBits - kSubBits)) & ((1u << (kSubBits + 1)) - 2u)));
+        if (se) {
+            *sym = se & 0xffu;
+            return se >> 8;
+        }
+    }
     return long_code(win, __ldg(a.wlut + (win >> (32 - kLutBits))) & 0xffffu, a.nodes, sym);
+}
+// Byte offset of the table entry (32 bit) for the window at bit pos (< 64) of hi:lo.
+__device__ __forceinline__ uint32_t entry_offset(const BitBuf &b, uint32_t pos) {
+    return (window64(b, pos) >> (30 - kLutBits)) & ((kLutSize - 1) << 2);
 }
 
 // Count walk over `nwords` stream words whose first word is at shared address addr0, starting at
 // bit pos0 (< 32) of that word.  Consumes every symbol that begins before the end of the last
 // word.  Returns the symbol count; *exit_bits = bits past that end at which the walk stopped.
 // Walk state c: bits 0-6 position relative to b.hi (below 64 inside the main loop, up to 95 at the
-// very end), bits 9+ symbols.  Table entries (16 bit):
-// bits consumed | symbols << 9 for every whole code in the window, 0 = the first code is longer
-// than the window (the state does not move; the second lookup of a pair then reads 0 as well).
-__device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, uint32_t pos0, uint32_t clut_s,
+// very end), bits 9+ symbols.  Table entries (32 bit, shared): low half = bits consumed |
+// symbols << 9 for every whole code in the window, 0 = the first code is longer than the window
+// (the state does not move; the second lookup of a pair then reads 0 as well); high half = the
+// same for the first code alone, or for a marker 0x8000 | second-level slot / kNoSlot.
+__device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, uint32_t pos0, uint32_t clut_s, uint32_t sub_s,
                                                const DecArgs &a, uint32_t *exit_bits) {
     BitBuf b;
     buf_open(b, addr0);
     uint32_t c = pos0;
     const uint32_t limit = addr0 + 4u * (nwords + 1u);  // b.addr == limit: hi:lo are the last two words
     while (b.addr < limit) {
-        c += lds_u16(clut_s + ((window64(b, c) >> (31 - kLutBits)) & ((kLutSize - 1) << 1)));
-        const uint32_t e2 = lds_u16(clut_s + ((window64(b, c) >> (31 - kLutBits)) & ((kLutSize - 1) << 1)));
+        c += lds_u16(clut_s + entry_offset(b, c));
+        const uint32_t e2 = lds_u16(clut_s + entry_offset(b, c));
         c += e2;
         if (e2 == 0) {  // rare: a code of more than 12 bits
             if (c & 32u) {
@@ -642,7 +669,7 @@ __device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, 
                 c -= 32u;
             }
             uint32_t sym;
-            const uint32_t len = long_code_at(b, c & 31u, a, &sym);
+            const uint32_t len = long_code_at(b, c & 31u, lds_u16(clut_s + entry_offset(b, c) + 2u), sub_s, a, &sym);
             c += len ? (len | (1u << 9)) : 1u;
         }
         if (c & 32u) {
@@ -653,7 +680,7 @@ __device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, 
     // the last words: hi:lo end 64 or 32 bits short of the chunk's end (32: a long code crossed a word at the very end)
     uint32_t end_rel = 32u * (nwords + 3u) - 8u * (b.addr - addr0);
     while ((c & 127u) + kLutBits <= end_rel) {  // whole windows that cannot cross the end
-        const uint32_t e = lds_u16(clut_s + ((window64(b, c) >> (31 - kLutBits)) & ((kLutSize - 1) << 1)));
+        const uint32_t e = lds_u16(clut_s + entry_offset(b, c));
         if (e == 0) break;
         c += e;
     }
@@ -664,11 +691,10 @@ __device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, 
             c -= 32u;
             end_rel -= 32u;
         }
-        const uint32_t win = __funnelshift_l(b.lo, b.hi, c & 31u);
-        uint32_t add = __ldg(a.clut + (win >> (32 - kLutBits))) >> 16;
-        if (add & kLutMarker) {
+        uint32_t add = lds_u16(clut_s + entry_offset(b, c) + 2u);
+        if (add & 0x8000u) {
             uint32_t sym;
-            const uint32_t len = long_code(win, __ldg(a.wlut + (win >> (32 - kLutBits))) & 0xffffu, a.nodes, &sym);
+            const uint32_t len = long_code_at(b, c & 31u, add, sub_s, a, &sym);
             add = len ? (len | (1u << 9)) : 1u;
         }
         c += add;
@@ -720,28 +746,93 @@ __device__ __forceinline__ Region region_of(const DecArgs &a, uint32_t r) {
     return g;
 }
 
-// Count walk of a chunk that is not in an interior region (the ends of the stream): generic walker.
-__device__ __noinline__ void edge_count(const DecArgs &a, uint32_t gc, uint32_t start, bool known, uint32_t *entry,
-                                        uint32_t *cnt, uint32_t *exit_bits) {
-    const Chunk k = chunk_of(a, gc);
-    uint64_t pos = k.begin + start;
-    uint32_t bad = 0, dummy = 0;
-    if (!known && k.begin >= a.byte_lo * 8 + 128) {
-        pos = walk_generic<false>(a, k.begin - 128, k.begin, a.end_bit, &dummy, 0, &bad);
-        if (pos < k.begin) pos = k.begin;
+// ------------------------------------------------------------------ the ends of the stream
+// Regions that touch the ends of the stream (the first one, the last ones) are staged with guarded
+// loads — bytes outside the readable range read as zero — and their chunks are walked from the
+// same shared image.  A chunk that lies wholly inside the owned stream with at least 32 bits of
+// stream after it takes the fast walkers like any other; the others (the last chunk of the
+// stream, a first chunk whose known start is not in its first word) are walked one symbol at a
+// time with every limit checked, from the shared tables.
+__device__ __forceinline__ void region_stage_guarded(const DecArgs &a, uint64_t region_byte, uint32_t img_s, uint32_t lane) {
+    for (uint32_t v = lane; v < kImgVecs; v += 32) {
+        const long long byte = (long long)region_byte - 16 + 16ll * v;  // region 0 starts at byte 0: its run-up is not stream
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (byte >= (long long)a.byte_lo && byte + 16 <= (long long)a.byte_hi) {
+            w = swap4(ld_stream_v4(a.body_aligned + byte));
+        } else if (byte + 16 > (long long)a.byte_lo && byte < (long long)a.byte_hi) {
+            const long long lo = (long long)a.byte_lo - byte, hi = (long long)a.byte_hi - byte;
+            w = swap4(ld_partial_v4(a.body_aligned + byte, (int)(lo > 0 ? lo : 0), (int)(hi < 16 ? hi : 16)));
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(img_s + v * 16), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
     }
-    *entry = (uint32_t)(pos - k.begin);
-    *cnt = 0;
-    if (pos < k.end) pos = walk_generic<false>(a, pos, k.end, a.end_bit, cnt, 0, &bad);
-    *exit_bits = pos > k.end ? (uint32_t)(pos - k.end) : 0u;
+}
+
+struct LaneGeom {
+    uint32_t own_bits;   // symbols that begin in the first own_bits bits of the chunk are this chunk's (1056 unless the owned stream ends inside)
+    uint32_t hard_bits;  // no code may extend past this bit of the chunk (the end of the stream), clamped
+    bool fast;           // whole chunk owned and far enough from the end of the stream for the fast walkers
+    bool runup;          // the 128 bits before the chunk are stream
+};
+__device__ __forceinline__ LaneGeom lane_geom(const DecArgs &a, uint32_t gc) {
+    LaneGeom l;
+    const uint64_t begin = a.grid_bit + (uint64_t)gc * (kLaneBytes * 8);
+    const uint64_t own = a.own_end_bit > begin ? a.own_end_bit - begin : 0, hard = a.end_bit > begin ? a.end_bit - begin : 0;
+    l.own_bits = own < kLaneBytes * 8 ? (uint32_t)own : kLaneBytes * 8;
+    l.hard_bits = hard < 4096 ? (uint32_t)hard : 4096u;
+    l.fast = l.own_bits == kLaneBytes * 8 && l.hard_bits >= kLaneBytes * 8 + 32;
+    l.runup = begin >= a.byte_lo * 8 + 32 * kRunupWords;
+    return l;
+}
+
+// One symbol at bit `pos` of the chunk whose first word is at shared address chunk_s.  single_add: the
+// first-code half of the count table's entry layout (length | 1 << 9, or a marker).  Returns the code's
+// length (0 = no code here).
+__device__ __forceinline__ uint32_t edge_symbol(uint32_t chunk_s, uint32_t pos, uint32_t clut_s, uint32_t sub_s, const DecArgs &a,
+                                                uint32_t *sym, bool want_sym, uint32_t wlut_s) {
+    BitBuf b;
+    b.hi = lds_u32(chunk_s + 4u * (pos >> 5));
+    b.lo = lds_u32(chunk_s + 4u * (pos >> 5) + 4u);
+    b.nxt = 0;
+    b.addr = 0;
+    const uint32_t off = entry_offset(b, pos & 31u);
+    if (want_sym) {
+        const uint32_t e = lds_u32(wlut_s + off);
+        if (e >= 0x10000u) {
+            *sym = e & 0xffu;
+            return (e >> 23) & 15u;
+        }
+        return long_code_at(b, pos & 31u, e, sub_s, a, sym);
+    }
+    const uint32_t add = lds_u16(clut_s + off + 2u);
+    if (!(add & 0x8000u)) return add & 0x3fu;
+    return long_code_at(b, pos & 31u, add, sub_s, a, sym);
+}
+// Count walk with every limit checked (same rules as walk_generic).
+__device__ __noinline__ uint32_t lane_count_edge(uint32_t chunk_s, uint32_t start, const LaneGeom &l, uint32_t clut_s, uint32_t sub_s,
+                                                 const DecArgs &a, uint32_t *exit_bits) {
+    uint32_t pos = start, cnt = 0;
+    while (pos < l.own_bits) {
+        uint32_t sym;
+        const uint32_t len = edge_symbol(chunk_s, pos, clut_s, sub_s, a, &sym, false, 0);
+        if (len == 0) {  // no code here (incomplete dictionary): skip one bit, like every other walker
+            pos += 1;
+            continue;
+        }
+        if (pos + len > l.hard_bits) break;  // final pad bits look like the start of a longer code
+        pos += len;
+        cnt += 1;
+    }
+    *exit_bits = pos > l.own_bits ? pos - l.own_bits : 0u;
+    return cnt;
 }
 
 // Round 0 runs persistent (grid = resident CTAs, every warp strides over the regions, the table is
 // filled once per CTA); the repair rounds are launched one region per warp so that CTAs with
 // nothing to repair leave before they touch the table.
-__global__ void __launch_bounds__(kSyncWarps * 32, 5) region_sync_kernel(const DecArgs a, uint32_t n_regions, int round) {
-    __shared__ __align__(16) uint16_t clut_sh[kLutSize];
-    __shared__ __align__(16) uint8_t img[kSyncWarps][kImgBytes];
+__global__ void __launch_bounds__(kSyncWarps * 32, 2) region_sync_kernel(const DecArgs a, uint32_t n_regions, int round) {
+    extern __shared__ __align__(16) uint8_t dyn[];  // count table | second-level tables | one stream image per warp
+    uint32_t *clut_sh = reinterpret_cast<uint32_t *>(dyn);
+    uint16_t *sub_sh = reinterpret_cast<uint16_t *>(dyn + kLutSize * 4);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t stride = gridDim.x * kSyncWarps;
     uint32_t r = blockIdx.x * kSyncWarps + warp;
@@ -751,11 +842,13 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 5) region_sync_kernel(const D
         if (!__syncthreads_or(work)) return;
     }
     for (int i = threadIdx.x; i < kLutSize; i += kSyncWarps * 32) {
-        const uint32_t e = a.clut[i] & 0xffffu;
-        clut_sh[i] = (e & kLutMarker) ? 0 : (uint16_t)e;
+        const uint32_t e = a.clut[i];
+        clut_sh[i] = (e & kLutMarker) ? ((uint32_t)(a.slots[i] == kNoSlot ? kNoSlot : (0x8000u | a.slots[i])) << 16) : e;
     }
+    for (uint32_t i = threadIdx.x; i < kSubBytes / 2; i += kSyncWarps * 32) sub_sh[i] = a.slots[kLutSize + i];
     __syncthreads();
-    const uint32_t img_s = smem_addr(img[warp]), clut_s = smem_addr(clut_sh);
+    const uint32_t clut_s = pinned(smem_addr(clut_sh)), sub_s = pinned(smem_addr(sub_sh));
+    const uint32_t img_s = pinned(smem_addr(dyn) + kTableBytes + warp * kImgBytes);
     for (; r < n_regions; r += stride) {
         const uint32_t gc = r * 32 + lane;
         uint32_t start = 0;
@@ -785,13 +878,35 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 5) region_sync_kernel(const D
                 const uint32_t chunk_s = img_s + 16 + lane * kLaneBytes;
                 if (!known) {
                     uint32_t e;
-                    (void)lane_count(chunk_s - 4 * kRunupWords, kRunupWords, 0u, clut_s, a, &e);
+                    (void)lane_count(chunk_s - 4 * kRunupWords, kRunupWords, 0u, clut_s, sub_s, a, &e);
                     entry = e;
                 }
-                cnt = lane_count(chunk_s, kLaneWords, entry, clut_s, a, &exit_bits);
+                uint32_t mid_bits;
+                const uint32_t cnt_a = lane_count(chunk_s, kSplitWords, entry, clut_s, sub_s, a, &mid_bits);
+                cnt = cnt_a + lane_count(chunk_s + 4 * kSplitWords, kLaneWords - kSplitWords, mid_bits, clut_s, sub_s, a, &exit_bits);
+                a.mid[gc] = mid_bits | (cnt_a << 16);
             }
-        } else if (work) {
-            edge_count(a, gc, start, known, &entry, &cnt, &exit_bits);
+        } else {
+            __syncwarp();
+            region_stage_guarded(a, g.begin_byte, img_s, lane);
+            __syncwarp();
+            if (work) {
+                const LaneGeom l = lane_geom(a, gc);
+                const uint32_t chunk_s = img_s + 16 + lane * kLaneBytes;
+                if (!known && l.runup) {
+                    uint32_t e;
+                    (void)lane_count(chunk_s - 4 * kRunupWords, kRunupWords, 0u, clut_s, sub_s, a, &e);
+                    entry = e;
+                }
+                if (l.fast && entry < 32u) {
+                    uint32_t mid_bits;
+                    const uint32_t cnt_a = lane_count(chunk_s, kSplitWords, entry, clut_s, sub_s, a, &mid_bits);
+                    cnt = cnt_a + lane_count(chunk_s + 4 * kSplitWords, kLaneWords - kSplitWords, mid_bits, clut_s, sub_s, a, &exit_bits);
+                    a.mid[gc] = mid_bits | (cnt_a << 16);
+                } else {
+                    cnt = lane_count_edge(chunk_s, entry, l, clut_s, sub_s, a, &exit_bits);
+                }
+            }
         }
         if (work) {
             a.start_off[gc] = (uint16_t)entry;
@@ -884,75 +999,139 @@ __device__ __forceinline__ void lane_flush(const OutAcc &r, uint32_t a_begin) {
     }
 }
 
-// Table entries of the write walk (32 bit): symbols (one or two) in bits 0-15, bits consumed in
-// 16-21, 8 x symbols in 27-31; 0 = the first code is longer than the window.
-__device__ __forceinline__ void lane_write(uint32_t addr0, uint32_t nwords, uint32_t pos0, uint32_t wlut_s, const DecArgs &a,
-                                           OutAcc &r, uint32_t *bad) {
+// Table entries of the write walk (32 bit, shared): symbols (one or two) in bits 0-15, bits consumed
+// in 16-21, length of the first code in 23-26, 8 x symbols in 27-31.  A marker (first code longer
+// than the window) is 0x8000 | second-level slot or kNoSlot: nothing consumed, nothing appended.
+// Walk state c: bits 0-6 position relative to b.hi, the rest is noise from the adds.
+struct WriteWalk {
     BitBuf b;
-    buf_open(b, addr0);
-    uint32_t c = pos0;  // only bits 0-5 mean anything
-    const uint32_t limit = addr0 + 4u * (nwords + 1u);
-    while (b.addr < limit) {
-        const uint32_t e1 = lds_u32(wlut_s + ((window64(b, c) >> (30 - kLutBits)) & ((kLutSize - 1) << 2)));
-        c += e1 >> 16;
-        emit(r, e1, e1 >> 27);
-        const uint32_t e2 = lds_u32(wlut_s + ((window64(b, c) >> (30 - kLutBits)) & ((kLutSize - 1) << 2)));
-        c += e2 >> 16;
-        emit(r, e2, e2 >> 27);
-        if (e2 == 0) {
-            if (c & 32u) {
-                buf_shift(b);
-                c -= 32u;
-            }
-            uint32_t sym = 0;
-            const uint32_t len = long_code_at(b, c & 31u, a, &sym);
-            if (len) {
-                c += len;
-                emit(r, sym, 8u);
-            } else {
-                *bad = 1u;
-                c += 1u;
-            }
-        }
-        if (c & 32u) {
-            buf_shift(b);
-            c -= 32u;
-        }
+    uint32_t c, addr0, limit;
+    OutAcc r;
+};
+__device__ __forceinline__ void walk_open(WriteWalk &w, uint32_t addr0, uint32_t nwords, uint32_t pos0, uint32_t text_s) {
+    buf_open(w.b, addr0);
+    w.c = pos0;
+    w.addr0 = addr0;
+    w.limit = addr0 + 4u * (nwords + 1u);  // b.addr == limit: hi:lo are the last two words
+    w.r.lo = w.r.hi = 0;
+    w.r.A = text_s;
+}
+__device__ __forceinline__ uint32_t walk_lookup(WriteWalk &w, uint32_t wlut_s) {
+    const uint32_t e = lds_u32(wlut_s + entry_offset(w.b, w.c));
+    w.c += e >> 16;
+    emit(w.r, e, e >> 27);
+    return e;
+}
+__device__ __forceinline__ void walk_refill(WriteWalk &w) {
+    if (w.c & 32u) {
+        buf_shift(w.b);
+        w.c -= 32u;
     }
-    uint32_t end_rel = 32u * (nwords + 3u) - 8u * (b.addr - addr0);
-    while ((c & 127u) + kLutBits <= end_rel) {
-        const uint32_t e = lds_u32(wlut_s + ((window64(b, c) >> (30 - kLutBits)) & ((kLutSize - 1) << 2)));
-        if (e == 0) break;
-        c += e >> 16;
-        emit(r, e, e >> 27);
+}
+// The lookup before this did not move: a code of more than 12 bits (or no code at all).
+__device__ __forceinline__ void walk_long(WriteWalk &w, uint32_t wlut_s, uint32_t sub_s, const DecArgs &a, uint32_t *bad) {
+    walk_refill(w);
+    uint32_t sym = 0;
+    const uint32_t len = long_code_at(w.b, w.c & 31u, lds_u32(wlut_s + entry_offset(w.b, w.c)), sub_s, a, &sym);
+    if (len) {
+        w.c += len;
+        emit(w.r, sym, 8u);
+    } else {
+        *bad = 1u;
+        w.c += 1u;
+    }
+}
+// Two lookups, then at most one refill (a lookup consumes at most 12 bits).
+__device__ __forceinline__ void walk_pair(WriteWalk &w, uint32_t wlut_s, uint32_t sub_s, const DecArgs &a, uint32_t *bad) {
+    (void)walk_lookup(w, wlut_s);
+    if (walk_lookup(w, wlut_s) < 0x10000u) walk_long(w, wlut_s, sub_s, a, bad);
+    walk_refill(w);
+}
+// Whatever is left of the main loop, then the last words: whole windows while they cannot cross
+// the end, then one symbol at a time.
+__device__ __forceinline__ void walk_finish(WriteWalk &w, uint32_t nwords, uint32_t wlut_s, uint32_t sub_s, const DecArgs &a,
+                                            uint32_t *bad) {
+    while (w.b.addr < w.limit) walk_pair(w, wlut_s, sub_s, a, bad);
+    uint32_t end_rel = 32u * (nwords + 3u) - 8u * (w.b.addr - w.addr0);
+    while ((w.c & 127u) + kLutBits <= end_rel) {
+        const uint32_t e = lds_u32(wlut_s + entry_offset(w.b, w.c));
+        if (e < 0x10000u) break;
+        w.c += e >> 16;
+        emit(w.r, e, e >> 27);
     }
     for (;;) {
-        if ((c & 127u) >= end_rel) break;
-        if (c & 32u) {
-            buf_shift(b);
-            c -= 32u;
+        if ((w.c & 127u) >= end_rel) break;
+        if (w.c & 32u) {
+            buf_shift(w.b);
+            w.c -= 32u;
             end_rel -= 32u;
         }
-        const uint32_t win = __funnelshift_l(b.lo, b.hi, c & 31u);
-        const uint32_t idx = win >> (32 - kLutBits);
-        const uint32_t add = __ldg(a.clut + idx) >> 16;
-        uint32_t sym = lds_u32(wlut_s + idx * 4u) & 0xffu, len = add & 0xffu;
-        if (add & kLutMarker) {
-            len = long_code(win, __ldg(a.wlut + idx) & 0xffffu, a.nodes, &sym);
+        const uint32_t e = lds_u32(wlut_s + entry_offset(w.b, w.c));
+        uint32_t sym = e & 0xffu, len = (e >> 23) & 15u;
+        if (e < 0x10000u) {
+            len = long_code_at(w.b, w.c & 31u, e, sub_s, a, &sym);
             if (len == 0) {
                 *bad = 1u;
-                c += 1u;
+                w.c += 1u;
                 continue;
             }
         }
-        c += len;
+        w.c += len;
+        emit(w.r, sym, 8u);
+    }
+}
+// The write walk of one chunk: its two parts are decoded side by side (two independent dependency
+// chains per lane: the walk is a chain of dependent shifts and table loads, and a warp scheduler
+// with four warps cannot hide it otherwise).  chunk_s: shared address of the chunk's first word;
+// text_s: shared address of its first text byte; mid = entry of part two | symbols of part one << 16.
+__device__ __forceinline__ void lane_write(uint32_t chunk_s, uint32_t start, uint32_t mid, uint32_t text_s, uint32_t wlut_s,
+                                           uint32_t sub_s, const DecArgs &a, uint32_t *bad, OutAcc *ra, OutAcc *rb) {
+    WriteWalk wa, wb;
+    const uint32_t text_b = text_s + (mid >> 16);
+    walk_open(wa, chunk_s, kSplitWords, start, text_s);
+    walk_open(wb, chunk_s + 4 * kSplitWords, kLaneWords - kSplitWords, mid & 0xffffu, text_b);
+    while (wa.b.addr < wa.limit && wb.b.addr < wb.limit) {
+        (void)walk_lookup(wa, wlut_s);
+        (void)walk_lookup(wb, wlut_s);
+        const uint32_t ea = walk_lookup(wa, wlut_s);
+        const uint32_t eb = walk_lookup(wb, wlut_s);
+        if ((ea < eb ? ea : eb) < 0x10000u) {  // rare: one of them met a code of more than 12 bits
+            if (ea < 0x10000u) walk_long(wa, wlut_s, sub_s, a, bad);
+            if (eb < 0x10000u) walk_long(wb, wlut_s, sub_s, a, bad);
+        }
+        walk_refill(wa);
+        walk_refill(wb);
+    }
+    walk_finish(wa, kSplitWords, wlut_s, sub_s, a, bad);
+    walk_finish(wb, kLaneWords - kSplitWords, wlut_s, sub_s, a, bad);
+    *ra = wa.r;
+    *rb = wb.r;
+}
+// Write walk with every limit checked (a chunk at the ends of the stream): one symbol at a time.
+__device__ __noinline__ void lane_write_edge(uint32_t chunk_s, uint32_t start, const LaneGeom &l, uint32_t text_s, uint32_t wlut_s,
+                                             uint32_t sub_s, const DecArgs &a, uint32_t *bad, OutAcc *ra) {
+    OutAcc r;
+    r.lo = r.hi = 0;
+    r.A = text_s;
+    uint32_t pos = start;
+    while (pos < l.own_bits) {
+        uint32_t sym = 0;
+        const uint32_t len = edge_symbol(chunk_s, pos, 0, sub_s, a, &sym, true, wlut_s);
+        if (len == 0) {
+            *bad = 1u;
+            pos += 1;
+            continue;
+        }
+        if (pos + len > l.hard_bits) break;
+        pos += len;
         emit(r, sym, 8u);
     }
+    *ra = r;
 }
 
 // What the write walk of a region needs to know about it (loaded one region ahead).
 struct RegionMeta {
-    uint32_t cnt, start, prev_exit;
+    uint32_t cnt, start, prev_exit, mid;
     unsigned long long o_w;
     bool live;
 };
@@ -962,28 +1141,32 @@ __device__ __forceinline__ RegionMeta region_meta(const DecArgs &a, uint32_t r, 
     m.live = gc < a.n_chunks;
     m.cnt = m.live ? a.count[gc] : 0u;
     m.start = m.live ? a.start_off[gc] : 0u;
+    m.mid = m.live ? a.mid[gc] : 0u;
     m.prev_exit = (m.live && gc > 0) ? a.exit_off[gc - 1] : m.start;
     m.o_w = a.block_prefix[r];
     return m;
 }
 
-// Dynamic shared memory: write table (16 KiB) | per warp: stream image (kImgBytes) + text stage (stage_bytes).
+// Dynamic shared memory: write table (16 KiB) | second-level tables (8 KiB) | per warp: stream image (kImgBytes) + text stage (stage_bytes).
 // Persistent: one CTA per SM, every warp strides over the regions; the stream bytes and the
 // metadata of a warp's next region are requested before it walks the current one.
 __global__ void __launch_bounds__(512, 1) region_write_kernel(const DecArgs a, uint32_t n_regions, uint32_t stage_bytes) {
     extern __shared__ __align__(16) uint8_t dyn[];
     uint32_t *wlut_sh = reinterpret_cast<uint32_t *>(dyn);
+    uint16_t *sub_sh = reinterpret_cast<uint16_t *>(dyn + kLutSize * 4);
     for (uint32_t i = threadIdx.x; i < (uint32_t)kLutSize; i += blockDim.x) {
-        const uint32_t e = a.wlut[i], add = e >> 16;
-        wlut_sh[i] = (add & kLutMarker) ? 0u : ((e & 0xffffu) | ((add & 0xffu) << 16) | ((add >> 9) << 30));
+        const uint32_t e = a.wlut[i], add = e >> 16, len0 = (a.clut[i] >> 16) & 0xffu;
+        wlut_sh[i] = (add & kLutMarker) ? (uint32_t)(a.slots[i] == kNoSlot ? kNoSlot : (0x8000u | a.slots[i]))
+                                        : ((e & 0xffffu) | ((add & 0xffu) << 16) | (len0 << 23) | ((add >> 9) << 30));
     }
+    for (uint32_t i = threadIdx.x; i < kSubBytes / 2; i += blockDim.x) sub_sh[i] = a.slots[kLutSize + i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t stride = gridDim.x * (blockDim.x >> 5);
     uint32_t r = blockIdx.x * (blockDim.x >> 5) + warp;
     if (r >= n_regions) return;
-    const uint32_t img_s = smem_addr(dyn) + kLutSize * 4u + warp * (kImgBytes + stage_bytes);
-    const uint32_t stage_s = img_s + kImgBytes, wlut_s = smem_addr(wlut_sh);
+    const uint32_t img_s = pinned(smem_addr(dyn) + kTableBytes + warp * (kImgBytes + stage_bytes));
+    const uint32_t stage_s = pinned(img_s + kImgBytes), wlut_s = pinned(smem_addr(wlut_sh)), sub_s = pinned(smem_addr(sub_sh));
     uint32_t bad = 0;
 
     RegionMeta m = region_meta(a, r, lane);
@@ -1021,15 +1204,34 @@ __global__ void __launch_bounds__(512, 1) region_write_kernel(const DecArgs a, u
             const unsigned long long o_end = o_w + total < a.max_symbols ? o_w + total : a.max_symbols;
             uint8_t *dst_w = a.out + o_w;
             const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(dst_w) & 15u);  // text of other regions in the first vector
-            if (interior && skew + total <= stage_bytes) {
+            if (skew + total <= stage_bytes) {
+                if (!interior) {
+                    __syncwarp();
+                    region_stage_guarded(a, (a.grid_bit >> 3) + (uint64_t)r * kRegionBytes, img_s, lane);
+                }
                 __syncwarp();
-                OutAcc acc;
-                acc.lo = acc.hi = 0;
-                const uint32_t a_begin = stage_s + skew + (incl - cnt);
-                acc.A = a_begin;
-                if (cnt) lane_write(img_s + 16 + lane * kLaneBytes, kLaneWords, m_cur.start, wlut_s, a, acc, &bad);
+                const uint32_t text_s = stage_s + skew + (incl - cnt), chunk_s = img_s + 16 + lane * kLaneBytes;
+                OutAcc ra, rb;
+                ra.lo = ra.hi = rb.lo = rb.hi = 0;
+                ra.A = rb.A = text_s;
+                uint32_t text_b = text_s;  // where the second accumulator started
+                if (interior) {
+                    text_b = text_s + (m_cur.mid >> 16);
+                    lane_write(chunk_s, m_cur.start, m_cur.mid, text_s, wlut_s, sub_s, a, &bad, &ra, &rb);
+                } else if (m_cur.live && cnt) {
+                    const LaneGeom l = lane_geom(a, gc);
+                    if (l.fast && m_cur.start < 32u) {
+                        text_b = text_s + (m_cur.mid >> 16);
+                        lane_write(chunk_s, m_cur.start, m_cur.mid, text_s, wlut_s, sub_s, a, &bad, &ra, &rb);
+                    } else {
+                        lane_write_edge(chunk_s, m_cur.start, l, text_s, wlut_s, sub_s, a, &bad, &ra);
+                        rb.A = text_b = ra.A;
+                    }
+                }
+                // the bytes after the last whole word of either part leave once every lane has stored its whole words
                 __syncwarp();
-                if (cnt) lane_flush(acc, a_begin);
+                lane_flush(ra, text_s);
+                lane_flush(rb, text_b);
                 __syncwarp();
                 // the stage is an image of the text from the 16-byte boundary below dst_w: whole vectors leave as such
                 uint8_t *base = dst_w - skew;
@@ -1048,7 +1250,7 @@ __global__ void __launch_bounds__(512, 1) region_write_kernel(const DecArgs a, u
                         for (uint32_t k = lo; k < hi; ++k) base[k] = (uint8_t)lds_u8(stage_s + k);
                     }
                 }
-            } else if (m_cur.live && cnt) {  // the ends of the stream, or a region whose text does not fit the stage
+            } else if (m_cur.live && cnt) {  // a region whose text does not fit the stage (more than 227 KiB of shared memory holds)
                 const Chunk k = chunk_of(a, gc);
                 uint32_t n = 0;
                 if (k.begin + m_cur.start < k.end) walk_generic<true>(a, k.begin + m_cur.start, k.end, a.end_bit, &n, o, &bad);
@@ -1126,7 +1328,7 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t per = chunk_bytes == kLaneBytes ? 32 : kChunkThreads;  // chunks per scanned sum
     const uint64_t nb = (n + per - 1) / per;
     const uint64_t ng = (nb + kGroupRegions - 1) / kGroupRegions;
-    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2) + 64 + (size_t)ng * 8 + 64;
+    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 4) + 64 + (size_t)ng * 8 + 64;
 }
 
 // Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
@@ -1142,11 +1344,13 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uin
         if ((err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
         if ((err = cudaFuncSetAttribute(region_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess)
             return err;
+        if ((err = cudaFuncSetAttribute(region_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmem)) != cudaSuccess)
+            return err;
     }
     const uint32_t sync_blocks = (n_regions + kSyncWarps - 1) / kSyncWarps;
-    const uint32_t resident = (uint32_t)num_sms * 5u;  // __launch_bounds__(.., 5)
-    region_sync_kernel<<<sync_blocks < resident ? sync_blocks : resident, kSyncWarps * 32, 0, stream>>>(a, n_regions, 0);
-    region_sync_kernel<<<sync_blocks, kSyncWarps * 32, 0, stream>>>(a, n_regions, 1);
+    const uint32_t resident = (uint32_t)num_sms * 2u;  // __launch_bounds__(.., 2)
+    region_sync_kernel<<<sync_blocks < resident ? sync_blocks : resident, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 0);
+    region_sync_kernel<<<sync_blocks, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 1);
     if ((err = cudaMemsetAsync(a.changed, 0, 4, stream)) != cudaSuccess) return err;
     if (launches) *launches += 2;
     uint32_t rounds = 2;
@@ -1159,12 +1363,12 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uin
         if ((err = cudaMemcpyAsync(h_flag, a.max_sum, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
         if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
         // text stage of a warp: the largest region, 15 bytes of skew, whole vectors; as many warps as fit one SM
-        const uint32_t avail = (uint32_t)max_smem - kLutSize * 4u;
+        const uint32_t avail = (uint32_t)max_smem - kTableBytes;
         uint32_t stage = (*h_flag + 15u + 15u) & ~15u;
         if (stage + kImgBytes > avail) stage = (avail - kImgBytes) & ~15u;  // regions that do not fit take the generic walker
         uint32_t warps = avail / (stage + kImgBytes);
         if (warps > 16u) warps = 16u;
-        const uint32_t smem = kLutSize * 4u + warps * (stage + kImgBytes);
+        const uint32_t smem = kTableBytes + warps * (stage + kImgBytes);
         if (getenv("ET_DEBUG_LANES"))
             fprintf(stderr, "[lanes] regions=%u chunks=%u max_sum=%u stage=%u warps=%u smem=%u rounds=%u\n", n_regions, a.n_chunks,
                     *h_flag, stage, warps, smem, rounds);
@@ -1178,9 +1382,9 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uin
         if (*h_flag == 0) break;  // every entry was the true one: what the write walk produced stands
         // entries still moving: fixpoint rounds, four per host visit (the flag is cleared before the last of them)
         for (;;) {
-            for (int i = 0; i < 3; ++i) region_sync_kernel<<<sync_blocks, kSyncWarps * 32, 0, stream>>>(a, n_regions, (int)rounds + i);
+            for (int i = 0; i < 3; ++i) region_sync_kernel<<<sync_blocks, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + i);
             if ((err = cudaMemsetAsync(a.changed, 0, 4, stream)) != cudaSuccess) return err;
-            region_sync_kernel<<<sync_blocks, kSyncWarps * 32, 0, stream>>>(a, n_regions, (int)rounds + 3);
+            region_sync_kernel<<<sync_blocks, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + 3);
             rounds += 4;
             if (launches) *launches += 4;
             if ((err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
@@ -1196,7 +1400,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uin
 }
 
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
-                          const uint32_t *d_nodes, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
+                          const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
                           uint32_t *h_flag, cudaStream_t stream, int *launches, uint32_t *rounds_out) {
     const uint64_t n64 = chunk_count(g, chunk_bytes);
     uint8_t *p = static_cast<uint8_t *>(scratch_base);
@@ -1221,6 +1425,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.clut = d_clut;
     a.wlut = d_wlut;
     a.nodes = d_nodes;
+    a.slots = d_slots;
     // [pad(4) | error flags(4) | total(8) | changed(4) | pad(4) | entry/exit(8)] then the arrays
     a.error_flags = reinterpret_cast<uint32_t *>(p + 4);
     a.total = reinterpret_cast<unsigned long long *>(p + 8);
@@ -1231,7 +1436,8 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.count = reinterpret_cast<uint32_t *>(p + 64 + (size_t)nb * 8);
     a.start_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 4);
     a.exit_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 6);
-    a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 8 + 63) & ~(size_t)63));
+    a.mid = reinterpret_cast<uint32_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 8);
+    a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 12 + 63) & ~(size_t)63));
     a.out = d_out;
     a.max_symbols = max_symbols;
 
