@@ -88,6 +88,18 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+// Loads from the decode tables: filled once per CTA before the walks, read-only afterwards, so the
+// compiler may schedule these freely among the (volatile) stores of the text.
+__device__ __forceinline__ uint32_t lds_tab_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_tab_u16(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -631,7 +643,7 @@ __device__ __forceinline__ uint32_t long_code_at(const BitBuf &b, uint32_t pos, 
                                                  const DecArgs &a, uint32_t *sym) {
     const uint32_t win = __funnelshift_l(b.lo, b.hi, pos);
     if (slot_e != kNoSlot) {
-        const uint32_t se = lds_u16(sub_s + ((slot_e & (kMaxSubTables - 1)) << (kSubBits + 1)) +
+        const uint32_t se = lds_tab_u16(sub_s + ((slot_e & (kMaxSubTables - 1)) << (kSubBits + 1)) +
                                     ((win >> (31 - kLutBits - kSubBits)) & ((1u << (kSubBits + 1)) - 2u)));
         if (se) {
             *sym = se & 0xffu;
@@ -660,8 +672,8 @@ __device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, 
     uint32_t c = pos0;
     const uint32_t limit = addr0 + 4u * (nwords + 1u);  // b.addr == limit: hi:lo are the last two words
     while (b.addr < limit) {
-        c += lds_u16(clut_s + entry_offset(b, c));
-        const uint32_t e2 = lds_u16(clut_s + entry_offset(b, c));
+        c += lds_tab_u16(clut_s + entry_offset(b, c));
+        const uint32_t e2 = lds_tab_u16(clut_s + entry_offset(b, c));
         c += e2;
         if (e2 == 0) {  // rare: a code of more than 12 bits
             if (c & 32u) {
@@ -669,7 +681,7 @@ __device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, 
                 c -= 32u;
             }
             uint32_t sym;
-            const uint32_t len = long_code_at(b, c & 31u, lds_u16(clut_s + entry_offset(b, c) + 2u), sub_s, a, &sym);
+            const uint32_t len = long_code_at(b, c & 31u, lds_tab_u16(clut_s + entry_offset(b, c) + 2u), sub_s, a, &sym);
             c += len ? (len | (1u << 9)) : 1u;
         }
         if (c & 32u) {
@@ -680,7 +692,7 @@ __device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, 
     // the last words: hi:lo end 64 or 32 bits short of the chunk's end (32: a long code crossed a word at the very end)
     uint32_t end_rel = 32u * (nwords + 3u) - 8u * (b.addr - addr0);
     while ((c & 127u) + kLutBits <= end_rel) {  // whole windows that cannot cross the end
-        const uint32_t e = lds_u16(clut_s + entry_offset(b, c));
+        const uint32_t e = lds_tab_u16(clut_s + entry_offset(b, c));
         if (e == 0) break;
         c += e;
     }
@@ -691,7 +703,7 @@ __device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, 
             c -= 32u;
             end_rel -= 32u;
         }
-        uint32_t add = lds_u16(clut_s + entry_offset(b, c) + 2u);
+        uint32_t add = lds_tab_u16(clut_s + entry_offset(b, c) + 2u);
         if (add & 0x8000u) {
             uint32_t sym;
             const uint32_t len = long_code_at(b, c & 31u, add, sub_s, a, &sym);
@@ -826,9 +838,8 @@ __device__ __noinline__ uint32_t lane_count_edge(uint32_t chunk_s, uint32_t star
     return cnt;
 }
 
-// Round 0 runs persistent (grid = resident CTAs, every warp strides over the regions, the table is
-// filled once per CTA); the repair rounds are launched one region per warp so that CTAs with
-// nothing to repair leave before they touch the table.
+// Persistent: grid = resident CTAs, every warp strides over the regions, the tables are filled once
+// per CTA.  A repair round first looks whether any of the CTA's regions has an entry that moved.
 __global__ void __launch_bounds__(kSyncWarps * 32, 2) region_sync_kernel(const DecArgs a, uint32_t n_regions, int round) {
     extern __shared__ __align__(16) uint8_t dyn[];  // count table | second-level tables | one stream image per warp
     uint32_t *clut_sh = reinterpret_cast<uint32_t *>(dyn);
@@ -836,10 +847,14 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 2) region_sync_kernel(const D
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t stride = gridDim.x * kSyncWarps;
     uint32_t r = blockIdx.x * kSyncWarps + warp;
-    if (round != 0) {  // one region per warp: is there anything to repair in this CTA?
-        const uint32_t gc = r * 32 + lane;
-        const bool work = gc > 0 && gc < a.n_chunks && a.exit_off[gc - 1] != a.start_off[gc];
-        if (!__syncthreads_or(work)) return;
+    if (round != 0) {  // is there anything to repair among this CTA's regions?  (usually not: leave before touching the tables)
+        bool any = false;
+#pragma unroll 4
+        for (uint32_t rr = r; rr < n_regions; rr += stride) {
+            const uint32_t gc = rr * 32 + lane;
+            any |= gc > 0 && gc < a.n_chunks && a.exit_off[gc - 1] != a.start_off[gc];
+        }
+        if (!__syncthreads_or(any)) return;
     }
     for (int i = threadIdx.x; i < kLutSize; i += kSyncWarps * 32) {
         const uint32_t e = a.clut[i];
@@ -989,6 +1004,17 @@ __device__ __forceinline__ void emit(OutAcc &r, uint32_t syms, uint32_t sh) {
     if ((r.A ^ a2) & 4u) sts_u32((a2 & ~3u) - 4u, __funnelshift_l(r.lo, r.hi, a2 << 3));
     r.A = a2;
 }
+// The same for the symbols of two table entries at once (up to four symbols, 8 x symbols in the top
+// five bits of either entry): at most one word is completed.
+__device__ __forceinline__ void emit_pair(OutAcc &r, uint32_t e1, uint32_t e2) {
+    const uint32_t s1 = e1 >> 27, s12 = s1 + (e2 >> 27);
+    const uint32_t syms = (e1 & 0xffffu) | (e2 << s1);  // bits of e2 above its symbols land above the 8 x (symbols) bits that are used
+    r.lo = __funnelshift_rc(r.lo, r.hi, s12);
+    r.hi = __funnelshift_rc(r.hi, syms, s12);
+    const uint32_t a2 = r.A + (s12 >> 3);
+    if ((r.A ^ a2) & 4u) sts_u32((a2 & ~3u) - 4u, __funnelshift_l(r.lo, r.hi, a2 << 3));
+    r.A = a2;
+}
 // The bytes after the lane's last whole word (at most 3, never before a_begin), one at a time.
 __device__ __forceinline__ void lane_flush(const OutAcc &r, uint32_t a_begin) {
     uint32_t k = r.A & 3u;
@@ -1016,12 +1042,6 @@ __device__ __forceinline__ void walk_open(WriteWalk &w, uint32_t addr0, uint32_t
     w.r.lo = w.r.hi = 0;
     w.r.A = text_s;
 }
-__device__ __forceinline__ uint32_t walk_lookup(WriteWalk &w, uint32_t wlut_s) {
-    const uint32_t e = lds_u32(wlut_s + entry_offset(w.b, w.c));
-    w.c += e >> 16;
-    emit(w.r, e, e >> 27);
-    return e;
-}
 __device__ __forceinline__ void walk_refill(WriteWalk &w) {
     if (w.c & 32u) {
         buf_shift(w.b);
@@ -1032,7 +1052,7 @@ __device__ __forceinline__ void walk_refill(WriteWalk &w) {
 __device__ __forceinline__ void walk_long(WriteWalk &w, uint32_t wlut_s, uint32_t sub_s, const DecArgs &a, uint32_t *bad) {
     walk_refill(w);
     uint32_t sym = 0;
-    const uint32_t len = long_code_at(w.b, w.c & 31u, lds_u32(wlut_s + entry_offset(w.b, w.c)), sub_s, a, &sym);
+    const uint32_t len = long_code_at(w.b, w.c & 31u, lds_tab_u32(wlut_s + entry_offset(w.b, w.c)), sub_s, a, &sym);
     if (len) {
         w.c += len;
         emit(w.r, sym, 8u);
@@ -1043,8 +1063,12 @@ __device__ __forceinline__ void walk_long(WriteWalk &w, uint32_t wlut_s, uint32_
 }
 // Two lookups, then at most one refill (a lookup consumes at most 12 bits).
 __device__ __forceinline__ void walk_pair(WriteWalk &w, uint32_t wlut_s, uint32_t sub_s, const DecArgs &a, uint32_t *bad) {
-    (void)walk_lookup(w, wlut_s);
-    if (walk_lookup(w, wlut_s) < 0x10000u) walk_long(w, wlut_s, sub_s, a, bad);
+    const uint32_t e1 = lds_tab_u32(wlut_s + entry_offset(w.b, w.c));
+    w.c += e1 >> 16;
+    const uint32_t e2 = lds_tab_u32(wlut_s + entry_offset(w.b, w.c));
+    w.c += e2 >> 16;
+    emit_pair(w.r, e1, e2);
+    if (e2 < 0x10000u) walk_long(w, wlut_s, sub_s, a, bad);
     walk_refill(w);
 }
 // Whatever is left of the main loop, then the last words: whole windows while they cannot cross
@@ -1054,7 +1078,7 @@ __device__ __forceinline__ void walk_finish(WriteWalk &w, uint32_t nwords, uint3
     while (w.b.addr < w.limit) walk_pair(w, wlut_s, sub_s, a, bad);
     uint32_t end_rel = 32u * (nwords + 3u) - 8u * (w.b.addr - w.addr0);
     while ((w.c & 127u) + kLutBits <= end_rel) {
-        const uint32_t e = lds_u32(wlut_s + entry_offset(w.b, w.c));
+        const uint32_t e = lds_tab_u32(wlut_s + entry_offset(w.b, w.c));
         if (e < 0x10000u) break;
         w.c += e >> 16;
         emit(w.r, e, e >> 27);
@@ -1066,7 +1090,7 @@ __device__ __forceinline__ void walk_finish(WriteWalk &w, uint32_t nwords, uint3
             w.c -= 32u;
             end_rel -= 32u;
         }
-        const uint32_t e = lds_u32(wlut_s + entry_offset(w.b, w.c));
+        const uint32_t e = lds_tab_u32(wlut_s + entry_offset(w.b, w.c));
         uint32_t sym = e & 0xffu, len = (e >> 23) & 15u;
         if (e < 0x10000u) {
             len = long_code_at(w.b, w.c & 31u, e, sub_s, a, &sym);
@@ -1091,10 +1115,14 @@ __device__ __forceinline__ void lane_write(uint32_t chunk_s, uint32_t start, uin
     walk_open(wa, chunk_s, kSplitWords, start, text_s);
     walk_open(wb, chunk_s + 4 * kSplitWords, kLaneWords - kSplitWords, mid & 0xffffu, text_b);
     while (wa.b.addr < wa.limit && wb.b.addr < wb.limit) {
-        (void)walk_lookup(wa, wlut_s);
-        (void)walk_lookup(wb, wlut_s);
-        const uint32_t ea = walk_lookup(wa, wlut_s);
-        const uint32_t eb = walk_lookup(wb, wlut_s);
+        const uint32_t ea1 = lds_tab_u32(wlut_s + entry_offset(wa.b, wa.c)), eb1 = lds_tab_u32(wlut_s + entry_offset(wb.b, wb.c));
+        wa.c += ea1 >> 16;
+        wb.c += eb1 >> 16;
+        const uint32_t ea = lds_tab_u32(wlut_s + entry_offset(wa.b, wa.c)), eb = lds_tab_u32(wlut_s + entry_offset(wb.b, wb.c));
+        wa.c += ea >> 16;
+        wb.c += eb >> 16;
+        emit_pair(wa.r, ea1, ea);
+        emit_pair(wb.r, eb1, eb);
         if ((ea < eb ? ea : eb) < 0x10000u) {  // rare: one of them met a code of more than 12 bits
             if (ea < 0x10000u) walk_long(wa, wlut_s, sub_s, a, bad);
             if (eb < 0x10000u) walk_long(wb, wlut_s, sub_s, a, bad);
@@ -1349,8 +1377,9 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uin
     }
     const uint32_t sync_blocks = (n_regions + kSyncWarps - 1) / kSyncWarps;
     const uint32_t resident = (uint32_t)num_sms * 2u;  // __launch_bounds__(.., 2)
-    region_sync_kernel<<<sync_blocks < resident ? sync_blocks : resident, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 0);
-    region_sync_kernel<<<sync_blocks, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 1);
+    const uint32_t sync_grid = sync_blocks < resident ? sync_blocks : resident;
+    region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 0);
+    region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 1);
     if ((err = cudaMemsetAsync(a.changed, 0, 4, stream)) != cudaSuccess) return err;
     if (launches) *launches += 2;
     uint32_t rounds = 2;
@@ -1382,9 +1411,9 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uin
         if (*h_flag == 0) break;  // every entry was the true one: what the write walk produced stands
         // entries still moving: fixpoint rounds, four per host visit (the flag is cleared before the last of them)
         for (;;) {
-            for (int i = 0; i < 3; ++i) region_sync_kernel<<<sync_blocks, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + i);
+            for (int i = 0; i < 3; ++i) region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + i);
             if ((err = cudaMemsetAsync(a.changed, 0, 4, stream)) != cudaSuccess) return err;
-            region_sync_kernel<<<sync_blocks, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + 3);
+            region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + 3);
             rounds += 4;
             if (launches) *launches += 4;
             if ((err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
