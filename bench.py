@@ -78,11 +78,13 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_for(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture, if any."""
+def traffic_for(kernels, workload="text-1G"):
+    """dram bytes (read + write) of one launch of each of `kernels`, summed, from the committed ncu --set full
+    capture of this workload (profiles/traffic.json, written by tools/profile_summary.py); None if not captured."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t.get(kernel)
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload, {})
+        vals = [t[k] for k in kernels]
+        return int(sum(vals))
     except Exception:
         return None
 
@@ -403,15 +405,17 @@ def run_ours(args, rank, world):
     c_dec = c_local if world == 1 else arm.own_body  # compressed bytes this rank decodes
     peak, peak_src = peaks()
 
-    def roof(kernel, alg_bytes, ms):
+    def roof(label, kernels, alg_bytes, ms):
         ach = alg_bytes / 1e9 / (ms / 1e3) if ms > 0 else 0.0
-        return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic_for(kernel), "algorithmic_bytes": alg_bytes, "ms": ms, "peak_source": peak_src}
+        traffic = traffic_for(kernels) if (world == 1 and args.workload == "text-1G") else None
+        return {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "algorithmic_bytes": alg_bytes, "ms": ms, "peak_source": peak_src}
 
-    roofs = [roof("pack (tile_bits_kernel + pack_kernel)", n + c_local, pack_ms),
-             roof("unpack (chunk_sync_kernel + chunk_write_kernel)", c_dec + got, unpack_ms)]
+    roofs = [roof("pack (run_bits_kernel + pack_runs_kernel)", ["run_bits_kernel", "pack_runs_kernel"], n + c_local, pack_ms),
+             roof("unpack (region_sync_kernel + region_write_kernel)", ["region_sync_kernel", "region_write_kernel"],
+                  c_dec + got, unpack_ms)]
     if world == 1:
-        roofs.insert(0, roof("histogram_kernel", n, hist_ms))
+        roofs.insert(0, roof("histogram_kernel", ["histogram_kernel"], n, hist_ms))
     dominant = max(roofs, key=lambda r: r["ms"])
 
     # ---- end to end with pinned HOST buffers (copies inside the timed region)

@@ -187,7 +187,7 @@ int pack_dev(et_ctx *ctx, const void *d_in, size_t n, const et_codebook &cb, uin
     if (rc != ET_OK) return rc;
     const PackScratch ps = pack_scratch_carve(ctx->d_scratch, g.num_tiles);
     int launches = 0;
-    ET_CUDA(ctx, launch_pack(g, ctx->d_small + kOffPackTables, wide, d_body, bit_phase, ps, ctx->d_scratch, sb,
+    ET_CUDA(ctx, launch_pack(g, ctx->d_small + kOffPackTables, wide, cb.max_length, d_body, bit_phase, ps, ctx->d_scratch, sb,
                              ctx->num_sms, s, &launches));
     ctx->launches += (uint64_t)launches;
     return ET_OK;

@@ -38,7 +38,8 @@ size_t pack_scratch_bytes(uint32_t num_tiles);
 PackScratch pack_scratch_carve(void *base, uint32_t num_tiles);
 
 // d_tables: narrow -> 256 x {code, len} (u32 pairs); wide -> 256 x u64 codes followed by 256 x u8 lengths.
-cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint8_t *d_out, uint32_t bit_phase,
+// max_len: longest code (sizes the bit image of a warp on the narrow path).
+cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint32_t max_len, uint8_t *d_out, uint32_t bit_phase,
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
                         cudaStream_t stream, int *launches);
 

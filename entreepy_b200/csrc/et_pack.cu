@@ -1,30 +1,35 @@
 // K2 — body pack (replaces encode.zig:303-318) and the seam fix-up.
 //
-// One pass over the input, per tile of 4096 symbols (256 threads x one 16-byte load):
-//   (1) per-symbol table lookup (code,len); adjacent symbols are fused into PAIRS
-//       ((code_a << len_b) | code_b, len_a + len_b) kept in registers,
-//   (2) block scan of per-thread bit totals; the tile total goes to the decoupled look-back
-//       chain, which returns the tile's bit offset in the output,
-//   (3) each thread shifts its 8 pairs into a 64-bit accumulator and ORs whole 32-bit words
-//       into a shared-memory image of the tile's bitstream at TILE-RELATIVE positions, so
-//       the assembly does not wait for the look-back,
-//   (4) the image is funnel-shifted to the tile's final bit position, byte-swapped to stream
-//       order (big-endian bit packing) and written with aligned 16-byte stores.
-// The lookup table is replicated for 16 lanes (entry (sym, lane & 15) at sym*128 + lane*8):
-// a 64-bit shared load is served half a warp at a time, so no lookup ever has a bank conflict
-// whatever the symbols are.
+// Codes of at most 32 bits (every dictionary the reference emits faithfully) take the lane-run
+// path: two streaming passes with warps as the unit of work, nothing waits at a block-wide
+// barrier.
+//   pass A  run_bits_kernel   bits of every run of 64 consecutive symbols, of the regions
+//                             (32 runs = 2048 symbols) before each region inside its group of
+//                             regions, and of every group;
+//   scan    group_scan_kernel one block: bits before every group;
+//   pass B  pack_runs_kernel  persistent warps, one region at a time.  A lane owns one run: its
+//                             bit offset inside the region comes from a warp scan of the run
+//                             totals; per symbol one conflict-free 64-bit shared load of
+//                             {code, len} (table replicated for 16 lanes: entry (sym, lane & 15)
+//                             at sym*128 + lane*8, a 64-bit load is served half a warp at a
+//                             time); adjacent symbols are fused into pairs when they fit 32
+//                             bits; everything goes through one 64-bit accumulator whose whole
+//                             words are ORed straight into their place in the warp's shared bit
+//                             image; the image is funnel-shifted to the region's final bit
+//                             position, byte-swapped to stream order (big-endian bit packing)
+//                             and stored as aligned 16-byte vectors.
+// A single-pass decoupled look-back was built first and measured: the chain of descriptors could
+// not retire more than ~64 tiles/us.  With the offsets known from pass A every region is independent.
+// Codes longer than 32 bits (where the reference itself emits truncated paths) use
+// the wide kernel further down (4096-symbol tiles, look-back).
 //
-// The fast path needs every pair to fit 32 bits (always, in practice: a code longer than 16
-// bits occurs less than once in 2^16 symbols) and a tile that lies wholly inside the input;
-// any other tile takes the per-symbol path.  Codes longer than 32 bits (where the reference
-// itself emits truncated paths) use the wide kernel further down.
+// Regions own whole output bytes only.  The (at most two) bytes a region shares with its
+// neighbours go to seam_head/seam_tail and are merged by seam_fixup_kernel, so the output needs no
+// pre-zeroing and no global atomics, and regions with zero bits (the symbol the reference drops
+// when all 256 byte values occur) are handled.
 //
-// Tiles own whole output bytes only.  The (at most two) bytes a tile shares with its
-// neighbours go to seam_head/seam_tail and are merged by seam_fixup_kernel, so the output
-// needs no pre-zeroing and no global atomics, and tiles with zero bits (the symbol the
-// reference drops when all 256 byte values occur) are handled.
-//
-// Algorithmic HBM bytes per symbol: 1 read + len/8 written (text: 1.586 B/symbol).
+// Algorithmic HBM bytes per symbol: 1 read + len/8 written (text: 1.586 B/symbol); pass A reads
+// the text a second time (not credited).
 #include "et_device.cuh"
 #include "et_kernels.cuh"
 
@@ -64,6 +69,9 @@ struct PackArgs {
     uint32_t group_tiles;              // tiles per group (a power of two)
     uint32_t group_shift;              // log2(group_tiles)
     uint32_t interior_lo, interior_hi; // tiles [lo, hi) lie wholly inside the input
+    uint16_t *run_bits;                // [32 * regions] lane-run pack: bits of every run of 64 symbols
+    uint32_t n_regions;                // lane-run pack: regions of 2048 symbols (one warp each)
+    uint32_t image_words;              // lane-run pack: words of a warp's bit image (guard included)
 };
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane) {
@@ -105,25 +113,10 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
 constexpr int kTableLanes = 16;
 constexpr int kTableBytes = 256 * kTableLanes * 8;                    // 32 KiB
 constexpr int kStageGuard = 4;                                        // zero words in front of the image
-constexpr int kStageWords = kStageGuard + kPackTileSyms + 8;          // worst case 32 bits per symbol
-constexpr int kPairs = kPackItems / 2;
 
 struct PackShared {
     uint32_t warp_sum[kWarps];
 };
-
-// (acc << len) | code on a 64-bit accumulator, len 0..32, then hand a finished 32-bit word to
-// the staging image when there is one.
-__device__ __forceinline__ void push_bits(uint32_t &hi, uint32_t &lo, uint32_t &fill, uint32_t *&wp, uint32_t code,
-                                          uint32_t len) {
-    hi = __funnelshift_lc(lo, hi, len);
-    lo = __funnelshift_lc(0u, lo, len) | code;
-    fill += len;
-    if (fill >= 32u) {
-        fill -= 32u;
-        atomicOr(wp++, __funnelshift_r(lo, hi, fill));
-    }
-}
 
 // 16 input bytes of thread `tid` of `tile`, and which of them exist (edge tiles only).
 __device__ __forceinline__ uint4 load_symbols(const PackArgs &a, uint32_t tile, uint32_t tid, bool interior,
@@ -140,35 +133,97 @@ __device__ __forceinline__ uint4 load_symbols(const PackArgs &a, uint32_t tile, 
     *valid = (0xffffu >> (16 - h)) & (0xffffu << l);
     return ld_partial_v4(a.in_aligned + v0, l, h);
 }
-__device__ __forceinline__ bool tile_is_interior(const PackArgs &a, uint32_t tile) {
-    return tile >= a.interior_lo && tile < a.interior_hi;
+// ---- scan: bits before each group (one block; groups are sized so that there are at most a few thousand).
+__global__ void __launch_bounds__(1024) group_scan_kernel(const PackArgs a, uint32_t n_groups) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n_groups + 1023u) / 1024u;
+    const uint32_t g_lo = min(t * per, n_groups), g_hi = min(g_lo + per, n_groups);
+    unsigned long long sum = 0;
+    for (uint32_t g = g_lo; g < g_hi; ++g) sum += a.group_prefix[g];
+    part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long v = t >= (uint32_t)d ? part[t - d] : 0ull;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[t] - sum + a.bit_phase;
+    for (uint32_t g = g_lo; g < g_hi; ++g) {
+        const unsigned long long gs = a.group_prefix[g];
+        a.group_prefix[g] = run;
+        run += gs;
+    }
 }
 
-// ---- pass A: one CTA per group of tiles.  For every tile: the bits the earlier tiles of the
-// group emit; for the group: its total.  Streaming: 16 B per thread, 16 byte-table lookups.
-__global__ void __launch_bounds__(kPackThreads) tile_bits_kernel(const PackArgs a) {
+// ------------------------------------------------------------------ lane-run pack (codes <= 32 bits)
+// The same two passes with warps instead of CTAs as the unit, so that nothing waits at a
+// block-wide barrier and the per-tile overhead (block scan, three barriers, image zeroing by the
+// whole CTA) is gone:
+//   pass A  run_bits_kernel: one streaming pass; bits of every RUN of 64 consecutive symbols
+//           (u16), of every region of 32 runs before it inside its group, of every group;
+//   scan    group_scan_kernel (one block);
+//   pass B  pack_runs_kernel: persistent warps.  A lane owns one run: four 16-byte loads, its
+//           bit offset inside the region from a warp scan of the run totals, then the 64
+//           symbols go through one 64-bit accumulator straight to their place in the warp's
+//           shared bit image.  The image is shifted to the region's bit position, swapped to
+//           stream order and stored as aligned 16-byte vectors; the two bytes a region may
+//           share with its neighbours take the seam arrays, as above.
+constexpr int kRunSyms = 64;
+constexpr int kRegionSyms = 32 * kRunSyms;  // 2048
+constexpr int kRunWarps = 8;
+
+__device__ __forceinline__ bool region_is_interior(const PackArgs &a, uint32_t r) {
+    return r >= a.interior_lo && r < a.interior_hi;
+}
+
+// (acc << len) | code on a 64-bit accumulator, len 0..32.  pos is the absolute BIT address of the next bit
+// in shared memory (byte address x 8 + bit, MSB first inside a word); when it crosses a word boundary the
+// 32 bits before the boundary are complete and are ORed into the image under a predicate — no branch, the
+// lanes of a warp stay together whatever their code lengths are.
+struct BitAcc {
+    uint32_t hi, lo, pos;
+};
+__device__ __forceinline__ void push_acc(BitAcc &b, uint32_t code, uint32_t len) {
+    b.hi = __funnelshift_lc(b.lo, b.hi, len);
+    b.lo = __funnelshift_lc(0u, b.lo, len) | code;
+    const uint32_t p2 = b.pos + len;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %0, 32;\n\tsetp.ne.u32 p, t, 0;\n\t@p red.shared.or.b32 [%1], %2;\n\t}" ::"r"(
+            b.pos ^ p2),
+        "r"(((p2 >> 3) & ~3u) - 4u), "r"(__funnelshift_r(b.lo, b.hi, p2))
+        : "memory");
+    b.pos = p2;
+}
+
+// Pass A.  A CTA iteration covers a slab of 4096 symbols = two regions (warps 0-3 / 4-7); thread t holds
+// 16 symbols, four neighbouring threads make a run.
+__global__ void __launch_bounds__(kPackThreads) run_bits_kernel(const PackArgs a) {
     __shared__ uint32_t len_sh[256 * 32];  // [sym][lane]: a warp-wide lookup never has a bank conflict
     __shared__ uint32_t warp_sum[2][4 * kWarps];
     for (int i = threadIdx.x; i < 256 * 32; i += kPackThreads) len_sh[i] = static_cast<const uint2 *>(a.tables)[i >> 5].y;
     __syncthreads();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t *len_lane = reinterpret_cast<const uint8_t *>(len_sh) + lane * 4;
-    const uint32_t t_lo = blockIdx.x * a.group_tiles, t_hi = min(t_lo + a.group_tiles, a.num_tiles);
+    const uint32_t n_slabs = (a.n_regions + 1) / 2, group_slabs = a.group_tiles / 2;
+    const uint32_t s_lo = blockIdx.x * group_slabs, s_hi = min(s_lo + group_slabs, n_slabs);
+    const uint32_t slab_int_lo = (a.interior_lo + 1) / 2, slab_int_hi = a.interior_hi / 2;  // slabs wholly inside the input
     uint32_t run = 0;  // bits of the group so far (same value in every thread)
-    constexpr int kBatch = 4;  // tiles per iteration: four independent 16-byte loads in flight per thread
-    for (uint32_t t0 = t_lo; t0 < t_hi; t0 += kBatch) {
+    constexpr int kBatch = 4;  // slabs per iteration: four independent 16-byte loads in flight per thread
+    for (uint32_t s0 = s_lo; s0 < s_hi; s0 += kBatch) {
         uint4 raw[kBatch];
         uint32_t valid[kBatch];
         bool interior[kBatch];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-            const uint32_t tile = t0 + b;
-            interior[b] = tile < t_hi && tile_is_interior(a, tile);
+            const uint32_t slab = s0 + b;
+            interior[b] = slab < s_hi && slab >= slab_int_lo && slab < slab_int_hi;
             valid[b] = 0xffffu;
             if (interior[b])
-                raw[b] = ld_stream_v4(a.in_aligned + (uint64_t)tile * kPackTileSyms + (uint64_t)tid * kPackItems);
-            else if (tile < t_hi)
-                raw[b] = load_symbols(a, tile, tid, false, &valid[b]);
+                raw[b] = ld_stream_v4(a.in_aligned + (uint64_t)slab * kPackTileSyms + (uint64_t)tid * kPackItems);
+            else if (slab < s_hi)
+                raw[b] = load_symbols(a, slab, tid, false, &valid[b]);
             else {
                 raw[b] = make_uint4(0, 0, 0, 0);
                 valid[b] = 0;
@@ -195,10 +250,13 @@ __global__ void __launch_bounds__(kPackThreads) tile_bits_kernel(const PackArgs 
                     bits[b] += ((valid[b] >> i) & 1u) ? len : 0u;
                 }
             }
+            bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], 1);
+            bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], 2);
+            if ((lane & 3u) == 0 && s0 + b < s_hi) a.run_bits[(size_t)(s0 + b) * 64 + (tid >> 2)] = (uint16_t)bits[b];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], o);
+            for (int o = 16; o > 2; o >>= 1) bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], o);
         }
-        uint32_t *ws = warp_sum[((t0 - t_lo) / kBatch) & 1];  // double-buffered: one barrier per batch
+        uint32_t *ws = warp_sum[((s0 - s_lo) / kBatch) & 1];  // double-buffered: one barrier per batch
         if (lane == 0) {
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) ws[b * kWarps + warp] = bits[b];
@@ -206,153 +264,140 @@ __global__ void __launch_bounds__(kPackThreads) tile_bits_kernel(const PackArgs 
         __syncthreads();
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-            if (tid == 0 && t0 + b < t_hi) a.tile_bits[t0 + b] = run;
 #pragma unroll
-            for (int q = 0; q < kWarps; ++q) run += ws[b * kWarps + q];
+            for (int h = 0; h < 2; ++h) {  // the two regions of the slab
+                const uint32_t r = 2 * (s0 + b) + h;
+                if (tid == 0 && s0 + b < s_hi && r < a.n_regions) a.tile_bits[r] = run;
+#pragma unroll
+                for (int q = 0; q < kWarps / 2; ++q) run += ws[b * kWarps + h * (kWarps / 2) + q];
+            }
         }
     }
     if (tid == 0) a.group_prefix[blockIdx.x] = run;  // group total; group_scan_kernel turns it into a prefix
 }
 
-// ---- scan: bits before each group (one block; groups are sized so that there are at most a few thousand).
-__global__ void __launch_bounds__(1024) group_scan_kernel(const PackArgs a, uint32_t n_groups) {
-    __shared__ unsigned long long part[1024];
-    const uint32_t t = threadIdx.x;
-    const uint32_t per = (n_groups + 1023u) / 1024u;
-    const uint32_t g_lo = min(t * per, n_groups), g_hi = min(g_lo + per, n_groups);
-    unsigned long long sum = 0;
-    for (uint32_t g = g_lo; g < g_hi; ++g) sum += a.group_prefix[g];
-    part[t] = sum;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        const unsigned long long v = t >= (uint32_t)d ? part[t - d] : 0ull;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
+// Four vectors of a lane's run and which of the 64 symbols exist (ragged ends of the input only).
+__device__ __forceinline__ void load_run(const PackArgs &a, uint32_t r, uint32_t lane, bool interior, uint4 (&raw)[4],
+                                         unsigned long long *valid) {
+    const uint64_t v0 = (uint64_t)r * kRegionSyms + (uint64_t)lane * kRunSyms;  // virtual byte index
+    *valid = ~0ull;
+    if (interior) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) raw[i] = ld_stream_v4(a.in_aligned + v0 + 16 * i);
+        return;
     }
-    unsigned long long run = part[t] - sum + a.bit_phase;
-    for (uint32_t g = g_lo; g < g_hi; ++g) {
-        const unsigned long long gs = a.group_prefix[g];
-        a.group_prefix[g] = run;
-        run += gs;
+    *valid = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long lo = (long long)a.misalign - (long long)(v0 + 16 * i), hi = (long long)a.v_end - (long long)(v0 + 16 * i);
+        const int l = (int)max(lo, 0ll), h = (int)min(hi, 16ll);
+        raw[i] = make_uint4(0, 0, 0, 0);
+        if (h > 0 && l < 16) {
+            raw[i] = ld_partial_v4(a.in_aligned + v0 + 16 * i, l, h);
+            *valid |= (unsigned long long)((0xffffu >> (16 - h)) & (0xffffu << l)) << (16 * i);
+        }
     }
 }
 
-// ---- pass B: every tile is independent (its first bit is known), so there is no waiting between CTAs.
-__global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
+// Pass B.  Dynamic shared memory: table (32 KiB, 16-lane replicated) | per warp: bit image | per warp: 32 edge bytes.
+__global__ void __launch_bounds__(kRunWarps * 32, 3) pack_runs_kernel(const PackArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *table = smem;                                              // [sym][lane & 15] x {code, len}
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + kTableBytes);
-    __shared__ PackShared sh;
-    __shared__ __align__(16) uint8_t edge_sh[2][16];  // first / last block of a tile, for bytewise stores
-
+    uint8_t *table = smem;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + kTableBytes) + (size_t)warp * a.image_words;
+    uint8_t *edge = smem + kTableBytes + (size_t)kRunWarps * a.image_words * 4 + warp * 32;
     {
         const uint2 *src = static_cast<const uint2 *>(a.tables);
         uint2 *dst = reinterpret_cast<uint2 *>(table);
-        for (int i = tid; i < 256 * kTableLanes; i += kPackThreads) dst[i] = src[i / kTableLanes];
-        for (int i = tid; i < kStageWords; i += kPackThreads) stage[i] = 0;
+        for (int i = tid; i < 256 * kTableLanes; i += kRunWarps * 32) dst[i] = src[i / kTableLanes];
+        for (uint32_t i = lane; i < a.image_words; i += 32) stage[i] = 0;
     }
     __syncthreads();
     const uint8_t *table_lane = table + (lane & (kTableLanes - 1)) * 8;
+    const uint32_t stride = gridDim.x * kRunWarps;
+    uint32_t r = blockIdx.x * kRunWarps + warp;
+    if (r >= a.n_regions) return;
 
-    // the next tile's 16 bytes are requested a whole tile ahead, so their DRAM latency is never waited for
-    uint32_t valid_next = 0xffffu;
-    uint4 raw_next = make_uint4(0, 0, 0, 0);
-    if (blockIdx.x < a.num_tiles) raw_next = load_symbols(a, blockIdx.x, tid, tile_is_interior(a, blockIdx.x), &valid_next);
-    for (uint32_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        // ---- (1) load + lookup
-        const bool interior = tile_is_interior(a, tile);  // uniform over the CTA
-        const uint32_t valid = valid_next;
-        const uint4 raw = raw_next;
-        if (tile + gridDim.x < a.num_tiles)
-            raw_next = load_symbols(a, tile + gridDim.x, tid, tile_is_interior(a, tile + gridDim.x), &valid_next);
-        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-        uint32_t pair_code[kPairs], pair_len[kPairs];
-        uint32_t my_bits = 0;
-        bool slow = !interior;
-        if (interior) {
-            uint32_t longest = 0;
-#pragma unroll
-            for (int j = 0; j < kPairs; ++j) {
-                const uint32_t w = rw[j >> 1];
-                const int sa = 16 * (j & 1), sb = sa + 8;
-                // byte -> byte offset sym*128 into this lane's column of the table
-                const uint32_t oa = sa == 0 ? ((w << 7) & 0x7f80u) : ((w >> (sa - 7)) & 0x7f80u);
-                const uint32_t ob = (w >> (sb - 7)) & 0x7f80u;
-                const uint2 ea = *reinterpret_cast<const uint2 *>(table_lane + oa);
-                const uint2 eb = *reinterpret_cast<const uint2 *>(table_lane + ob);
-                const uint32_t len = ea.y + eb.y;
-                longest = max(longest, len);
-                pair_len[j] = len;
-                pair_code[j] = __funnelshift_lc(0u, ea.x, eb.y) | eb.x;
-                my_bits += len;
-            }
-            slow = longest > 32u;
-        } else {  // ragged first or last tile: only the bit total is needed here, the per-symbol path below does the rest
-#pragma unroll
-            for (int j = 0; j < kPairs; ++j) pair_code[j] = pair_len[j] = 0;
-#pragma unroll 1
-            for (int i = 0; i < kPackItems; ++i) {
-                const uint32_t sym = (rw[i >> 2] >> (8 * (i & 3))) & 0xffu;
-                if ((valid >> i) & 1u) my_bits += reinterpret_cast<const uint2 *>(table_lane + sym * (kTableLanes * 8))->y;
-            }
+    // the next region's symbols and run total are requested before the current region is assembled
+    uint4 raw_next[4];
+    unsigned long long valid_next;
+    load_run(a, r, lane, region_is_interior(a, r), raw_next, &valid_next);
+    uint32_t bits_next = a.run_bits[(size_t)r * 32 + lane];
+    unsigned long long begin_next = a.group_prefix[r >> a.group_shift] + a.tile_bits[r];
+    for (;;) {
+        const bool interior = region_is_interior(a, r);
+        const uint4 raw[4] = {raw_next[0], raw_next[1], raw_next[2], raw_next[3]};
+        const unsigned long long valid = valid_next;
+        const uint32_t my_bits = bits_next;
+        const unsigned long long bit_begin = begin_next;
+        const uint32_t r_next = r + stride;
+        if (r_next < a.n_regions) {
+            load_run(a, r_next, lane, region_is_interior(a, r_next), raw_next, &valid_next);
+            bits_next = a.run_bits[(size_t)r_next * 32 + lane];
+            begin_next = a.group_prefix[r_next >> a.group_shift] + a.tile_bits[r_next];
         }
+        const uint32_t incl = warp_inclusive_scan(my_bits, lane);
+        const uint32_t region_bits = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t my_off = incl - my_bits;
+        const unsigned long long bit_end = bit_begin + region_bits;
+        if (lane == 0) a.tile_state[r] = bit_end;  // for the seam fix-up
 
-        // ---- (2) block scan of bit totals (and the sum of the earlier tiles of the group)
-        uint32_t incl = my_bits;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += up;
-        }
-        if (lane == 31) sh.warp_sum[warp] = incl;
-        // B_i: first bit of the tile in the output
-        const unsigned long long bit_begin = a.group_prefix[tile >> a.group_shift] + a.tile_bits[tile];
-        const bool tile_slow = __syncthreads_or(slow);  // B1
-        uint32_t warp_off = 0, tile_bits = 0;
-#pragma unroll
-        for (int q = 0; q < kWarps; ++q) {
-            const uint32_t s = sh.warp_sum[q];
-            if (q < (int)warp) warp_off += s;
-            tile_bits += s;
-        }
-        const uint32_t my_off = warp_off + incl - my_bits;  // first bit of this thread inside the tile
-        const unsigned long long bit_end = bit_begin + tile_bits;  // E_i
-        if (tid == 0) a.tile_state[tile] = bit_end;  // for the seam fix-up
-
-        // ---- (3) assemble at tile-relative positions: words hold stream bits MSB-first; all
-        // stores are ORs because the first and last word of a thread are shared with its neighbours
+        // ---- assemble at region-relative positions (words hold stream bits MSB-first; every store is an OR:
+        // the first and last word of a lane are shared with its neighbours)
         {
-            uint32_t fill = my_off & 31u;  // bits pending in the accumulator
-            uint32_t *wp = stage + kStageGuard + (my_off >> 5);
-            uint32_t hi = 0, lo = 0;
-            if (!tile_slow) {
+            BitAcc acc;
+            acc.hi = acc.lo = 0;
+            acc.pos = (uint32_t)__cvta_generic_to_shared(stage + kStageGuard) * 8u + my_off;
+            if (interior) {
+                uint4 v0 = raw[0], v1 = raw[1], v2 = raw[2], v3 = raw[3];
+#pragma unroll 1
+                for (int it = 0; it < 4; ++it) {  // one 16-byte vector per trip: the body must stay inside the instruction cache
+                    const uint32_t rw[4] = {v0.x, v0.y, v0.z, v0.w};
 #pragma unroll
-                for (int j = 0; j < kPairs; ++j) push_bits(hi, lo, fill, wp, pair_code[j], pair_len[j]);
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t w = rw[q];
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            const int sa = 16 * p, sb = sa + 8;
+                            const uint32_t oa = sa == 0 ? ((w << 7) & 0x7f80u) : ((w >> (sa - 7)) & 0x7f80u);
+                            const uint32_t ob = (w >> (sb - 7)) & 0x7f80u;
+                            const uint2 ea = *reinterpret_cast<const uint2 *>(table_lane + oa);
+                            const uint2 eb = *reinterpret_cast<const uint2 *>(table_lane + ob);
+                            const uint32_t len = ea.y + eb.y;
+                            if (len <= 32u) {
+                                push_acc(acc, __funnelshift_lc(0u, ea.x, eb.y) | eb.x, len);
+                            } else {  // rare: a pair of more than 32 bits goes in as two codes
+                                push_acc(acc, ea.x, ea.y);
+                                push_acc(acc, eb.x, eb.y);
+                            }
+                        }
+                    }
+                    v0 = v1;
+                    v1 = v2;
+                    v2 = v3;
+                }
             } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t w = rw[q], ok = valid >> (4 * q);
+                for (int q = 0; q < 16; ++q) {  // ragged ends of the input: one symbol at a time, only those that exist
+                    const uint4 v = raw[q >> 2];
+                    uint32_t w = (q & 3) == 0 ? v.x : (q & 3) == 1 ? v.y : (q & 3) == 2 ? v.z : v.w;
+                    uint32_t ok = (uint32_t)(valid >> (4 * q)) & 15u;
 #pragma unroll 1
                     for (int k = 0; k < 4; ++k, w >>= 8, ok >>= 1) {
                         const uint2 e = *reinterpret_cast<const uint2 *>(table_lane + (w & 0xffu) * (kTableLanes * 8));
-                        if (ok & 1u) push_bits(hi, lo, fill, wp, e.x, e.y);
+                        if (ok & 1u) push_acc(acc, e.x, e.y);
                     }
                 }
             }
-            if (fill) atomicOr(wp, lo << (32u - fill));
+            if (acc.pos & 31u) atomicOr(stage + kStageGuard + ((my_off + my_bits) >> 5), acc.lo << (32u - (acc.pos & 31u)));
         }
-        __syncthreads();  // B2: image complete
-        uint8_t *first_byte = a.out + (bit_begin >> 3);              // byte holding bit B_i
+        __syncwarp();  // image complete
+        uint8_t *first_byte = a.out + (bit_begin >> 3);              // byte holding the region's first bit
         const uint32_t align = (uint32_t)(reinterpret_cast<uintptr_t>(first_byte) & 15u);
         uint8_t *gbase = first_byte - align;                         // frame byte k <-> gbase[k]
-        const uint32_t shift = align * 8 + (uint32_t)(bit_begin & 7);  // frame bit of tile bit 0 (< 128)
-        const uint32_t used_bits = shift + tile_bits;
+        const uint32_t shift = align * 8 + (uint32_t)(bit_begin & 7);  // frame bit of region bit 0 (< 128)
+        const uint32_t used_bits = shift + region_bits;
         const uint32_t n_chunks = (used_bits + 127u) >> 7;
-
-        // ---- (4) move the image to its frame position, swap to stream order, store whole owned
-        // bytes, park the shared ones in the seam arrays
         {
             const unsigned long long byte0 = bit_begin >> 3;
             const unsigned long long full_lo = (bit_begin + 7) >> 3, full_hi = bit_end >> 3;  // owned bytes [lo,hi)
@@ -362,39 +407,41 @@ __global__ void __launch_bounds__(kPackThreads) pack_kernel(const PackArgs a) {
             const bool has_tail = (bit_end & 7) != 0 && full_hi >= full_lo;
             const uint32_t s_head = align;
             const uint32_t s_tail = (uint32_t)(full_hi - byte0) + align;  // only meaningful when has_tail
-            if (tid == 0) {
-                if (!has_head) a.seam_head[tile] = 0;
-                if (!has_tail) a.seam_tail[tile] = 0;
+            if (lane == 0) {
+                if (!has_head) a.seam_head[r] = 0;
+                if (!has_tail) a.seam_tail[r] = 0;
             }
-            // frame word f holds tile bits [32f - shift, 32f - shift + 32)
-            const uint32_t r = (32u - (shift & 31u)) & 31u;
-            const int back = (int)((shift + 31u) >> 5);  // image words the frame starts before the tile
-            for (uint32_t c = tid; c < n_chunks; c += kPackThreads) {
+            // frame word f holds region bits [32f - shift, 32f - shift + 32)
+            const uint32_t rot = (32u - (shift & 31u)) & 31u;
+            const int back = (int)((shift + 31u) >> 5);  // image words the frame starts before the region
+            for (uint32_t c = lane; c < n_chunks; c += 32) {
                 const uint32_t *src = stage + kStageGuard + (int)(4 * c) - back;
                 const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3], w4 = src[4];
                 uint4 v;
-                v.x = bswap32(__funnelshift_l(w1, w0, r));
-                v.y = bswap32(__funnelshift_l(w2, w1, r));
-                v.z = bswap32(__funnelshift_l(w3, w2, r));
-                v.w = bswap32(__funnelshift_l(w4, w3, r));
+                v.x = bswap32(__funnelshift_l(w1, w0, rot));
+                v.y = bswap32(__funnelshift_l(w2, w1, rot));
+                v.z = bswap32(__funnelshift_l(w3, w2, rot));
+                v.w = bswap32(__funnelshift_l(w4, w3, rot));
                 const uint32_t k0 = c * 16;
                 if (k0 >= s_lo && k0 + 16 <= s_hi) {
                     st_stream_v4(gbase + k0, v);
                 } else {
-                    // a block at the ragged start or end of the tile: through a small per-thread buffer
-                    uint4 *tmp = reinterpret_cast<uint4 *>(edge_sh[c == 0 ? 0 : 1]);
+                    // a block at the ragged start or end of the region: bytewise, through a small buffer
+                    uint4 *tmp = reinterpret_cast<uint4 *>(edge + (c == 0 ? 0 : 16));
                     *tmp = v;
                     const uint8_t *tb = reinterpret_cast<const uint8_t *>(tmp);
                     const uint32_t lo_k = max(k0, s_lo), hi_k = min(k0 + 16u, s_hi);
                     for (uint32_t kk = lo_k; kk < hi_k; ++kk) gbase[kk] = tb[kk - k0];
-                    if (has_head && s_head >= k0 && s_head < k0 + 16u) a.seam_head[tile] = tb[s_head - k0];
-                    if (has_tail && s_tail >= k0 && s_tail < k0 + 16u) a.seam_tail[tile] = tb[s_tail - k0];
+                    if (has_head && s_head >= k0 && s_head < k0 + 16u) a.seam_head[r] = tb[s_head - k0];
+                    if (has_tail && s_tail >= k0 && s_tail < k0 + 16u) a.seam_tail[r] = tb[s_tail - k0];
                 }
             }
         }
-        __syncthreads();  // B3: everyone has read the image
-        for (uint32_t i = tid; i < ((tile_bits + 31u) >> 5) + 1u; i += kPackThreads) stage[kStageGuard + i] = 0;
-        // the next tile's B1 separates this zeroing from the next assembly
+        __syncwarp();  // everyone has read the image
+        for (uint32_t i = lane; i < ((region_bits + 31u) >> 5) + 1u; i += 32) stage[kStageGuard + i] = 0;
+        __syncwarp();
+        if (r_next >= a.n_regions) break;
+        r = r_next;
     }
 }
 
@@ -628,10 +675,12 @@ static uint32_t pack_group_tiles(uint32_t num_tiles) {
     while (num_tiles / gt > 8192) gt <<= 1;
     return gt;
 }
+// The lane-run path cuts the input into regions of 2048 symbols (two per tile) and keeps a u16 per run of 64.
 size_t pack_scratch_bytes(uint32_t num_tiles) {
-    // [ticket + pad : 16][tile_state : 8*T][group_prefix : 8*G][tile_bits : 4*T][seam_head : T][seam_tail : T]
-    const size_t groups = ((size_t)num_tiles + 7) / 8;
-    return 16 + (size_t)num_tiles * 14 + groups * 8 + 16;
+    // [ticket + pad : 16][tile_state : 8*T][group_prefix : 8*G][tile_bits : 4*T][seam_head : T][seam_tail : T][run_bits : 64*T]
+    const size_t t = (size_t)num_tiles * 2 + 2;
+    const size_t groups = (t + 7) / 8;
+    return 16 + t * 14 + groups * 8 + 16 + t * 64 + 64;
 }
 PackScratch pack_scratch_carve(void *base, uint32_t num_tiles) {
     PackScratch s;
@@ -646,7 +695,7 @@ PackScratch pack_scratch_carve(void *base, uint32_t num_tiles) {
     return s;
 }
 
-cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint8_t *d_out, uint32_t bit_phase,
+cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint32_t max_len, uint8_t *d_out, uint32_t bit_phase,
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
                         cudaStream_t stream, int *launches) {
     if (g.num_tiles == 0) return cudaSuccess;
@@ -687,20 +736,46 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         if (launches) *launches += 1;
     } else {
         (void)scratch_bytes;
-        const int smem = kTableBytes + kStageWords * 4;
-        err = cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (err != cudaSuccess) return err;
-        a.group_tiles = pack_group_tiles(g.num_tiles);
+        // lane-run path: regions of 2048 symbols, carved from the same scratch block
+        const uint32_t n_regions = (uint32_t)((g.v_end + kRegionSyms - 1) / kRegionSyms);
+        const uint32_t r_alloc = 2 * g.num_tiles + 2;  // regions the slabs of pass A may touch
+        const PackScratch rs = pack_scratch_carve(scratch_base, r_alloc);
+        a.tile_state = rs.tile_state;
+        a.seam_head = rs.seam_head;
+        a.seam_tail = rs.seam_tail;
+        a.tile_bits = rs.tile_bits;
+        a.group_prefix = rs.group_prefix;
+        a.run_bits = reinterpret_cast<uint16_t *>(
+            (reinterpret_cast<uintptr_t>(rs.seam_tail + r_alloc) + 15) & ~(uintptr_t)15);
+        a.n_regions = n_regions;
+        a.num_tiles = n_regions;
+        a.interior_lo = g.misalign ? 1u : 0u;
+        a.interior_hi = (uint32_t)(g.v_end / kRegionSyms);
+        if (a.interior_hi < a.interior_lo) a.interior_hi = a.interior_lo;
+        a.image_words = (uint32_t)(kStageGuard + (kRegionSyms * max_len + 31) / 32 + 16 + 3) & ~3u;
+        a.group_tiles = pack_group_tiles(n_regions);
+        if (a.group_tiles < 2) a.group_tiles = 2;
         for (a.group_shift = 0; (1u << a.group_shift) < a.group_tiles; ++a.group_shift) {}
-        const uint32_t groups = (g.num_tiles + a.group_tiles - 1) / a.group_tiles;
-        tile_bits_kernel<<<groups, kPackThreads, 0, stream>>>(a);
+        const uint32_t groups = (n_regions + a.group_tiles - 1) / a.group_tiles;
+        run_bits_kernel<<<groups, kPackThreads, 0, stream>>>(a);
         group_scan_kernel<<<1, 1024, 0, stream>>>(a, groups);
+        const int smem = kTableBytes + kRunWarps * (int)a.image_words * 4 + kRunWarps * 32;
+        err = cudaFuncSetAttribute(pack_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (err != cudaSuccess) return err;
         int per_sm = (227 * 1024) / (smem + 1024);
-        if (per_sm > 2048 / kPackThreads) per_sm = 2048 / kPackThreads;
-        unsigned grid = (unsigned)num_sms * (unsigned)per_sm;  // persistent CTAs: the table is loaded once per CTA
-        if (grid > g.num_tiles) grid = g.num_tiles;
-        pack_kernel<<<grid, kPackThreads, smem, stream>>>(a);
+        if (per_sm > 3) per_sm = 3;  // __launch_bounds__(.., 3)
+        if (per_sm < 1) per_sm = 1;
+        unsigned grid = (unsigned)num_sms * (unsigned)per_sm;  // persistent warps: the table is loaded once per CTA
+        const unsigned need = (n_regions + kRunWarps - 1) / kRunWarps;
+        if (grid > need) grid = need;
+        pack_runs_kernel<<<grid, kRunWarps * 32, smem, stream>>>(a);
         if (launches) *launches += 3;
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        seam_fixup_kernel<<<(n_regions + 255) / 256, 256, 0, stream>>>(a.tile_state, a.seam_head, a.seam_tail, n_regions,
+                                                                     bit_phase, d_out);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
     }
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
