@@ -311,7 +311,17 @@ def run_ours(args, rank, world):
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the communicator prints "NCCL version ..." on stdout when it is created: stdout carries one JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     codec = et.Codec(local)
     n_total, kind = WORKLOADS[args.workload]
     plan = sharded.ShardPlan(n_total, world, rank)

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(const PackArgs a, uint
 //           share with its neighbours take the seam arrays, as above.
 constexpr int kRunSyms = 64;
 constexpr int kRegionSyms = 32 * kRunSyms;  // 2048
-constexpr int kRunWarps = 8;
+constexpr int kRunWarps = 16;
 
 __device__ __forceinline__ bool region_is_interior(const PackArgs &a, uint32_t r) {
     return r >= a.interior_lo && r < a.interior_hi;
@@ -300,7 +300,7 @@ __device__ __forceinline__ void load_run(const PackArgs &a, uint32_t r, uint32_t
 }
 
 // Pass B.  Dynamic shared memory: table (32 KiB, 16-lane replicated) | per warp: bit image | per warp: 32 edge bytes.
-__global__ void __launch_bounds__(kRunWarps * 32, 3) pack_runs_kernel(const PackArgs a) {
+__global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const PackArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *table = smem;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -318,24 +318,14 @@ __global__ void __launch_bounds__(kRunWarps * 32, 3) pack_runs_kernel(const Pack
     uint32_t r = blockIdx.x * kRunWarps + warp;
     if (r >= a.n_regions) return;
 
-    // the next region's symbols and run total are requested before the current region is assembled
-    uint4 raw_next[4];
-    unsigned long long valid_next;
-    load_run(a, r, lane, region_is_interior(a, r), raw_next, &valid_next);
-    uint32_t bits_next = a.run_bits[(size_t)r * 32 + lane];
-    unsigned long long begin_next = a.group_prefix[r >> a.group_shift] + a.tile_bits[r];
     for (;;) {
         const bool interior = region_is_interior(a, r);
-        const uint4 raw[4] = {raw_next[0], raw_next[1], raw_next[2], raw_next[3]};
-        const unsigned long long valid = valid_next;
-        const uint32_t my_bits = bits_next;
-        const unsigned long long bit_begin = begin_next;
+        uint4 raw[4];
+        unsigned long long valid;
+        load_run(a, r, lane, interior, raw, &valid);
+        const uint32_t my_bits = a.run_bits[(size_t)r * 32 + lane];
+        const unsigned long long bit_begin = a.group_prefix[r >> a.group_shift] + a.tile_bits[r];
         const uint32_t r_next = r + stride;
-        if (r_next < a.n_regions) {
-            load_run(a, r_next, lane, region_is_interior(a, r_next), raw_next, &valid_next);
-            bits_next = a.run_bits[(size_t)r_next * 32 + lane];
-            begin_next = a.group_prefix[r_next >> a.group_shift] + a.tile_bits[r_next];
-        }
         const uint32_t incl = warp_inclusive_scan(my_bits, lane);
         const uint32_t region_bits = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t my_off = incl - my_bits;
@@ -763,7 +753,7 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         err = cudaFuncSetAttribute(pack_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (err != cudaSuccess) return err;
         int per_sm = (227 * 1024) / (smem + 1024);
-        if (per_sm > 3) per_sm = 3;  // __launch_bounds__(.., 3)
+        if (per_sm > 2) per_sm = 2;  // __launch_bounds__(.., 2)
         if (per_sm < 1) per_sm = 1;
         unsigned grid = (unsigned)num_sms * (unsigned)per_sm;  // persistent warps: the table is loaded once per CTA
         const unsigned need = (n_regions + kRunWarps - 1) / kRunWarps;
