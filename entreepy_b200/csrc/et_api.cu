@@ -497,12 +497,11 @@ int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, 
     uint32_t rounds = 0;
     const uint16_t *d_slots = reinterpret_cast<const uint16_t *>(ctx->d_small + kOffSlots);
     ET_CUDA(ctx, launch_unpack(g, chunk_bytes, d_clut, d_wlut, d_nodes, d_slots, d_out, max_symbols, ctx->d_scratch,
-                               reinterpret_cast<uint32_t *>(ctx->h_small + kOffFlags + 32), s, &launches, &rounds));
+                               ctx->h_small + kOffFlags, s, &launches, &rounds));
     ctx->launches += (uint64_t)launches;
     ctx->last_decode_rounds = rounds;
-    // header of the scratch block: pad(4) | error flags(4) | symbols found(8) | changed(4) | pad(4) | entry, exit (4+4)
-    ET_CUDA(ctx, cudaMemcpyAsync(ctx->h_small + kOffFlags, ctx->d_scratch, 32, cudaMemcpyDeviceToHost, s));
-    ET_CUDA(ctx, cudaStreamSynchronize(s));
+    // launch_unpack left the stream idle and a copy of the scratch header in the pinned block:
+    // pad(4) | error flags(4) | symbols found(8) | changed(4) | largest region(4) | entry, exit (4+4)
     uint32_t flags = 0;
     unsigned long long total = 0;
     std::memcpy(&flags, ctx->h_small + kOffFlags + 4, 4);

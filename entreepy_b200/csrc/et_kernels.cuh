@@ -72,12 +72,13 @@ uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms, uint32_t min_l
 size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes);
 // Scratch header after the call: [4] error flags (u32), [8] symbols found (u64), [24] entry used
 // by the first chunk, [28] exit of the last chunk (u32 bits).  Writes min(total, max_symbols)
-// bytes to d_out.  Blocks on the stream between check rounds (h_flag: pinned host word).
+// bytes to d_out.  Blocks on the stream between check rounds; on return the stream is idle and
+// h_hdr (pinned host memory, 64 bytes) holds a copy of the first 32 bytes of the scratch header.
 // d_slots: UnpackTables::slot_of followed by UnpackTables::sub (second-level tables of the lane-interleaved decoder).
 // *rounds_out = passes over the chunk entries it took (2 = the guesses plus one repair round sufficed).
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
                           const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
-                          uint32_t *h_flag, cudaStream_t stream, int *launches, uint32_t *rounds_out);
+                          uint8_t *h_hdr, cudaStream_t stream, int *launches, uint32_t *rounds_out);
 
 // ---------------------------------------------------------------- synthetic input generator
 cudaError_t launch_synth(uint8_t *d_out, size_t n, uint64_t seed, uint64_t first_index, const uint32_t *d_thresholds,

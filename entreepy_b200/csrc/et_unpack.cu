@@ -1175,10 +1175,11 @@ __device__ __forceinline__ RegionMeta region_meta(const DecArgs &a, uint32_t r, 
     return m;
 }
 
-// Dynamic shared memory: write table (16 KiB) | second-level tables (8 KiB) | per warp: stream image (kImgBytes) + text stage (stage_bytes).
+// Dynamic shared memory (smem_bytes, all an SM has): write table (16 KiB) | second-level tables (8 KiB) | per warp:
+// stream image (kImgBytes) + text stage (sized on the device from the largest region).
 // Persistent: one CTA per SM, every warp strides over the regions; the stream bytes and the
 // metadata of a warp's next region are requested before it walks the current one.
-__global__ void __launch_bounds__(512, 1) region_write_kernel(const DecArgs a, uint32_t n_regions, uint32_t stage_bytes) {
+__global__ void __launch_bounds__(512, 1) region_write_kernel(const DecArgs a, uint32_t n_regions, uint32_t smem_bytes) {
     extern __shared__ __align__(16) uint8_t dyn[];
     uint32_t *wlut_sh = reinterpret_cast<uint32_t *>(dyn);
     uint16_t *sub_sh = reinterpret_cast<uint16_t *>(dyn + kLutSize * 4);
@@ -1190,8 +1191,16 @@ __global__ void __launch_bounds__(512, 1) region_write_kernel(const DecArgs a, u
     for (uint32_t i = threadIdx.x; i < kSubBytes / 2; i += blockDim.x) sub_sh[i] = a.slots[kLutSize + i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t stride = gridDim.x * (blockDim.x >> 5);
-    uint32_t r = blockIdx.x * (blockDim.x >> 5) + warp;
+    // text stage of a warp: the largest region of this stream (found by the scan, read here so that the host
+    // does not have to look at it), 15 bytes of skew, whole vectors; as many warps as then fit the SM work
+    const uint32_t avail = smem_bytes - kTableBytes;
+    uint32_t stage_bytes = (*a.max_sum + 15u + 15u) & ~15u;
+    if (stage_bytes + kImgBytes > avail) stage_bytes = (avail - kImgBytes) & ~15u;  // regions that do not fit take the generic walker
+    uint32_t warps = avail / (stage_bytes + kImgBytes);
+    if (warps > (blockDim.x >> 5)) warps = blockDim.x >> 5;
+    if (warp >= warps) return;
+    const uint32_t stride = gridDim.x * warps;
+    uint32_t r = blockIdx.x * warps + warp;
     if (r >= n_regions) return;
     const uint32_t img_s = pinned(smem_addr(dyn) + kTableBytes + warp * (kImgBytes + stage_bytes));
     const uint32_t stage_s = pinned(img_s + kImgBytes), wlut_s = pinned(smem_addr(wlut_sh)), sub_s = pinned(smem_addr(sub_sh));
@@ -1361,7 +1370,7 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
 
 // Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
 // look at the scratch header after the scan: the largest region sizes the text stage of a warp.
-static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uint32_t *h_flag, cudaStream_t stream,
+static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, const void *d_header, uint8_t *h_hdr, cudaStream_t stream,
                                        int *launches, uint32_t *rounds_out) {
     static int max_smem = 0, num_sms = 0;
     cudaError_t err;
@@ -1375,51 +1384,42 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uin
         if ((err = cudaFuncSetAttribute(region_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmem)) != cudaSuccess)
             return err;
     }
+    const uint32_t *h_changed = reinterpret_cast<const uint32_t *>(h_hdr + 16);
     const uint32_t sync_blocks = (n_regions + kSyncWarps - 1) / kSyncWarps;
     const uint32_t resident = (uint32_t)num_sms * 2u;  // __launch_bounds__(.., 2)
     const uint32_t sync_grid = sync_blocks < resident ? sync_blocks : resident;
     region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 0);
     region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 1);
-    if ((err = cudaMemsetAsync(a.changed, 0, 4, stream)) != cudaSuccess) return err;
+    if ((err = cudaMemsetAsync(a.changed, 0, 8, stream)) != cudaSuccess) return err;  // changed and max_sum
     if (launches) *launches += 2;
     uint32_t rounds = 2;
     for (;;) {
         const uint32_t n_groups = (n_regions + kGroupRegions - 1) / kGroupRegions;
-        if ((err = cudaMemsetAsync(a.max_sum, 0, 4, stream)) != cudaSuccess) return err;
         region_sum_kernel<<<n_groups, 1024, 0, stream>>>(a, n_regions);
         chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, a.group_prefix, n_groups);
         region_apply_kernel<<<n_groups, 1024, 0, stream>>>(a, n_regions);
-        if ((err = cudaMemcpyAsync(h_flag, a.max_sum, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
-        if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
-        // text stage of a warp: the largest region, 15 bytes of skew, whole vectors; as many warps as fit one SM
-        const uint32_t avail = (uint32_t)max_smem - kTableBytes;
-        uint32_t stage = (*h_flag + 15u + 15u) & ~15u;
-        if (stage + kImgBytes > avail) stage = (avail - kImgBytes) & ~15u;  // regions that do not fit take the generic walker
-        uint32_t warps = avail / (stage + kImgBytes);
-        if (warps > 16u) warps = 16u;
-        const uint32_t smem = kTableBytes + warps * (stage + kImgBytes);
-        if (getenv("ET_DEBUG_LANES"))
-            fprintf(stderr, "[lanes] regions=%u chunks=%u max_sum=%u stage=%u warps=%u smem=%u rounds=%u\n", n_regions, a.n_chunks,
-                    *h_flag, stage, warps, smem, rounds);
-        const uint32_t write_blocks = (n_regions + warps - 1) / warps;
-        region_write_kernel<<<write_blocks < (uint32_t)num_sms ? write_blocks : (uint32_t)num_sms, warps * 32, smem, stream>>>(
-            a, n_regions, stage);
+        const uint32_t write_blocks = (n_regions + 15u) / 16u;
+        region_write_kernel<<<write_blocks < (uint32_t)num_sms ? write_blocks : (uint32_t)num_sms, 512, max_smem, stream>>>(
+            a, n_regions, (uint32_t)max_smem);
         if (launches) *launches += 4;
-        if ((err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
+        // one look at the scratch header: error flags, symbols found, "an entry was wrong", entry and exit of the shard
+        if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
         if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
-        if (getenv("ET_DEBUG_LANES")) fprintf(stderr, "[lanes] after write: changed=%u\n", *h_flag);
-        if (*h_flag == 0) break;  // every entry was the true one: what the write walk produced stands
+        if (getenv("ET_DEBUG_LANES"))
+            fprintf(stderr, "[lanes] regions=%u chunks=%u max_sum=%u rounds=%u changed=%u\n", n_regions, a.n_chunks,
+                    *reinterpret_cast<const uint32_t *>(h_hdr + 20), rounds, *h_changed);
+        if (*h_changed == 0) break;  // every entry was the true one: what the write walk produced stands
         // entries still moving: fixpoint rounds, four per host visit (the flag is cleared before the last of them)
         for (;;) {
             for (int i = 0; i < 3; ++i) region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + i);
-            if ((err = cudaMemsetAsync(a.changed, 0, 4, stream)) != cudaSuccess) return err;
+            if ((err = cudaMemsetAsync(a.changed, 0, 8, stream)) != cudaSuccess) return err;
             region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + 3);
             rounds += 4;
             if (launches) *launches += 4;
-            if ((err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
+            if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
             if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
-            if (getenv("ET_DEBUG_LANES")) fprintf(stderr, "[lanes] repair rounds=%u changed=%u\n", rounds, *h_flag);
-            if (*h_flag == 0) break;
+            if (getenv("ET_DEBUG_LANES")) fprintf(stderr, "[lanes] repair rounds=%u changed=%u\n", rounds, *h_changed);
+            if (*h_changed == 0) break;
             if (rounds > a.n_chunks + 8u) return cudaErrorUnknown;  // cannot happen: each round settles one more chunk
         }
         if ((err = cudaMemsetAsync(a.error_flags, 0, 4, stream)) != cudaSuccess) return err;  // raised by a wrong parse
@@ -1430,13 +1430,17 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, uin
 
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
                           const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
-                          uint32_t *h_flag, cudaStream_t stream, int *launches, uint32_t *rounds_out) {
+                          uint8_t *h_hdr, cudaStream_t stream, int *launches, uint32_t *rounds_out) {
+    uint32_t *h_flag = reinterpret_cast<uint32_t *>(h_hdr + 32);  // a word for the check rounds
     const uint64_t n64 = chunk_count(g, chunk_bytes);
     uint8_t *p = static_cast<uint8_t *>(scratch_base);
     cudaError_t err = cudaMemsetAsync(p, 0, 64, stream);
     if (err != cudaSuccess) return err;
     if (rounds_out) *rounds_out = 0;
-    if (n64 == 0) return cudaSuccess;
+    if (n64 == 0) {  // nothing to decode: an all-zero header
+        for (int i = 0; i < 32; ++i) h_hdr[i] = 0;
+        return cudaStreamSynchronize(stream);
+    }
     const uint32_t n = (uint32_t)n64;
     const bool lanes = chunk_bytes == kLaneBytes;
     const uint32_t nb = lanes ? (n + 31u) / 32u : (n + kChunkThreads - 1) / kChunkThreads;
@@ -1470,7 +1474,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.out = d_out;
     a.max_symbols = max_symbols;
 
-    if (lanes) return launch_unpack_lanes(a, nb, h_flag, stream, launches, rounds_out);
+    if (lanes) return launch_unpack_lanes(a, nb, p, h_hdr, stream, launches, rounds_out);
 
     // Common case (codes that re-synchronise quickly): one walk from the guesses, one repair
     // round for the few chunks whose run-up was too short (text: 0.1 % of them; their exits do
@@ -1513,11 +1517,11 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
         chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, a.block_prefix, nb);
         chunk_write_kernel<<<nb, kChunkThreads, 0, stream>>>(a);
         if (launches) *launches += 3;
-        err = cudaMemcpyAsync(h_flag, a.changed, 4, cudaMemcpyDeviceToHost, stream);
+        err = cudaMemcpyAsync(h_hdr, p, 32, cudaMemcpyDeviceToHost, stream);  // the whole scratch header, for the caller as well
         if (err != cudaSuccess) return err;
         err = cudaStreamSynchronize(stream);
         if (err != cudaSuccess) return err;
-        if (*h_flag == 0) break;  // every entry was the true one: what the write walk produced stands
+        if (*reinterpret_cast<const uint32_t *>(h_hdr + 16) == 0) break;  // every entry was the true one: what the write walk produced stands
         err = settle();
         if (err != cudaSuccess) return err;
         // the error flags the first write walk may have raised came from a wrong parse
