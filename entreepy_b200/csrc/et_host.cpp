@@ -261,35 +261,45 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
     t->complete = kraft == (1ull << 32);
     for (uint32_t i = 0; i < n_nodes; ++i) t->nodes[i] = ((uint32_t)kid[i][1] << 16) | kid[i][0];
 
-    // First-level table: decode as many whole codes as fit in a kLutBits window.
+    // First-level table.  first[w] = (length << 8 | symbol) of the code that starts window w, filled code by
+    // code (a code of len bits owns 2^(kLutBits-len) windows); 0 = no code of at most kLutBits bits starts here.
+    static_assert(kLutBits <= 16, "window index fits 16 bits");
+    uint16_t first[kLutSize];
+    std::memset(first, 0, sizeof first);
+    for (uint32_t e = 0; e < dict.n_entries; ++e) {
+        const unsigned len = dict.length[e];
+        if (len > (unsigned)kLutBits) continue;
+        const uint32_t lo = (uint32_t)(dict.code[e] << (kLutBits - len)), n = 1u << (kLutBits - len);
+        for (uint32_t w = lo; w < lo + n; ++w) first[w] = (uint16_t)((len << 8) | dict.symbol[e]);
+    }
+    // windows that are a proper prefix of longer codes ("markers") and the trie node they stop at
+    uint16_t stuck[kLutSize];
+    for (uint32_t w = 0; w < (uint32_t)kLutSize; ++w) stuck[w] = (uint16_t)kChildNone;
+    for (uint32_t e = 0; e < dict.n_entries; ++e) {
+        const unsigned len = dict.length[e];
+        if (len <= (unsigned)kLutBits) continue;
+        const uint32_t w = (uint32_t)(dict.code[e] >> (len - kLutBits));
+        if (stuck[w] != kChildNone) continue;
+        uint32_t node = 0;
+        for (int b = kLutBits - 1; b >= 0; --b) node = kid[node][(w >> b) & 1u];  // an internal node: the code is longer
+        stuck[w] = (uint16_t)node;
+    }
+    // then as many whole codes as fit in the window, one table step per code
     for (uint32_t idx = 0; idx < (uint32_t)kLutSize; ++idx) {
         unsigned pos = 0, cnt = 0, len0 = 0, len01 = 0, sym0 = 0, sym1 = 0;
-        uint32_t stuck_node = kChildNone;
         for (;;) {
-            uint32_t node = 0;
-            unsigned p = pos;
-            int found = -1;
-            bool dead = false;
-            while (p < (unsigned)kLutBits) {
-                const unsigned b = (idx >> (kLutBits - 1 - p)) & 1u;
-                const uint32_t c = kid[node][b];
-                ++p;
-                if (c == kChildNone) { dead = true; break; }
-                if (c & kChildLeaf) { found = (int)(c & 0xFF); break; }
-                node = c;
-            }
-            if (found < 0) {
-                if (cnt == 0) stuck_node = dead ? kChildNone : node;
-                break;
-            }
-            if (cnt == 0) sym0 = (unsigned)found, len0 = p;
-            if (cnt == 1) sym1 = (unsigned)found, len01 = p;
-            pos = p;
+            const uint16_t f = first[(idx << pos) & (kLutSize - 1)];  // zeros shifted in: a code that ends inside them does not fit
+            const unsigned len = f >> 8;
+            if (len == 0 || pos + len > (unsigned)kLutBits) break;
+            if (cnt == 0) sym0 = f & 0xFFu, len0 = len;
+            if (cnt == 1) sym1 = f & 0xFFu, len01 = pos + len;
+            pos += len;
             ++cnt;
             if (pos >= (unsigned)kLutBits) break;
         }
         t->slot_of[idx] = kNoSlot;
         if (cnt == 0) {
+            const uint32_t stuck_node = stuck[idx];
             t->clut[idx] = kLutMarker | (kLutMarker << 16);
             t->wlut[idx] = (stuck_node & 0xFFFFu) | (kLutMarker << 16);
             if (stuck_node != kChildNone && t->n_slots < kMaxSubTables) {  // second level: the next 8 bits
