@@ -59,6 +59,8 @@ struct DecArgs {
     uint32_t *changed;            // [1]
     uint32_t *max_sum;            // [1] symbols of the largest region
     unsigned long long *group_prefix;  // [ceil(regions / 1024)] lane-interleaved decoder: scan of the group sums
+    uint32_t *work;               // [regions] lane-interleaved decoder: regions in which an entry has to be repaired
+    uint32_t *work_count;         // [1]
     uint32_t *error_flags;
     unsigned long long *total;
     uint32_t *entry_exit;
@@ -838,24 +840,34 @@ __device__ __noinline__ uint32_t lane_count_edge(uint32_t chunk_s, uint32_t star
     return cnt;
 }
 
-// Persistent: grid = resident CTAs, every warp strides over the regions, the tables are filled once
-// per CTA.  A repair round first looks whether any of the CTA's regions has an entry that moved.
+// Which regions hold a chunk whose recorded entry is not its left neighbour's recorded exit?  One warp looks at
+// four regions; the list it leaves is the work of the next repair round.
+__global__ void __launch_bounds__(256) region_check_kernel(const DecArgs a, uint32_t n_regions) {
+    const uint32_t lane = threadIdx.x & 31, w = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    bool bad[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t r = w * 4 + k, gc = r * 32 + lane;
+        bad[k] = r < n_regions && gc > 0 && gc < a.n_chunks && a.exit_off[gc - 1] != a.start_off[gc];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (__any_sync(0xffffffffu, bad[k]) && lane == 0) {
+            a.work[atomicAdd(a.work_count, 1u)] = w * 4 + k;
+            *a.changed = 1u;
+        }
+}
+
+// Persistent: grid = resident CTAs, every warp strides over the regions (round 0) or over the list
+// region_check_kernel left (repair rounds); the tables are filled once per CTA.
 __global__ void __launch_bounds__(kSyncWarps * 32, 2) region_sync_kernel(const DecArgs a, uint32_t n_regions, int round) {
     extern __shared__ __align__(16) uint8_t dyn[];  // count table | second-level tables | one stream image per warp
     uint32_t *clut_sh = reinterpret_cast<uint32_t *>(dyn);
     uint16_t *sub_sh = reinterpret_cast<uint16_t *>(dyn + kLutSize * 4);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t stride = gridDim.x * kSyncWarps;
-    uint32_t r = blockIdx.x * kSyncWarps + warp;
-    if (round != 0) {  // is there anything to repair among this CTA's regions?  (usually not: leave before touching the tables)
-        bool any = false;
-#pragma unroll 4
-        for (uint32_t rr = r; rr < n_regions; rr += stride) {
-            const uint32_t gc = rr * 32 + lane;
-            any |= gc > 0 && gc < a.n_chunks && a.exit_off[gc - 1] != a.start_off[gc];
-        }
-        if (!__syncthreads_or(any)) return;
-    }
+    const uint32_t n_items = round == 0 ? n_regions : *a.work_count;
+    if (blockIdx.x * kSyncWarps >= n_items) return;  // repair rounds: usually only a few CTAs have anything to do
     for (int i = threadIdx.x; i < kLutSize; i += kSyncWarps * 32) {
         const uint32_t e = a.clut[i];
         clut_sh[i] = (e & kLutMarker) ? ((uint32_t)(a.slots[i] == kNoSlot ? kNoSlot : (0x8000u | a.slots[i])) << 16) : e;
@@ -864,7 +876,8 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 2) region_sync_kernel(const D
     __syncthreads();
     const uint32_t clut_s = pinned(smem_addr(clut_sh)), sub_s = pinned(smem_addr(sub_sh));
     const uint32_t img_s = pinned(smem_addr(dyn) + kTableBytes + warp * kImgBytes);
-    for (; r < n_regions; r += stride) {
+    for (uint32_t item = blockIdx.x * kSyncWarps + warp; item < n_items; item += stride) {
+        const uint32_t r = round == 0 ? item : a.work[item];
         const uint32_t gc = r * 32 + lane;
         uint32_t start = 0;
         bool work = gc < a.n_chunks;
@@ -877,7 +890,6 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 2) region_sync_kernel(const D
             }
         }
         if (!__any_sync(0xffffffffu, work)) continue;
-        if (work && round != 0) *a.changed = 1u;
         if (gc == 0 && a.head_known) start = a.head_off;
         const bool known = round != 0 || (gc == 0 && a.head_known);
         const Region g = region_of(a, r);
@@ -885,7 +897,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 2) region_sync_kernel(const D
         if (g.interior) {
             RegionRegs q;
             region_load(a, g.begin_byte, lane, q);
-            if (r + stride < n_regions) region_prefetch_l2(a, g.begin_byte + (uint64_t)stride * kRegionBytes, lane);
+            if (round == 0 && r + stride < n_regions) region_prefetch_l2(a, g.begin_byte + (uint64_t)stride * kRegionBytes, lane);
             __syncwarp();  // the walk of the region before this one has left the image
             region_store(q, img_s, lane);
             __syncwarp();
@@ -1365,7 +1377,7 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t per = chunk_bytes == kLaneBytes ? 32 : kChunkThreads;  // chunks per scanned sum
     const uint64_t nb = (n + per - 1) / per;
     const uint64_t ng = (nb + kGroupRegions - 1) / kGroupRegions;
-    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 4) + 64 + (size_t)ng * 8 + 64;
+    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 4) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * 4 + 64;
 }
 
 // Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
@@ -1388,10 +1400,20 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
     const uint32_t sync_blocks = (n_regions + kSyncWarps - 1) / kSyncWarps;
     const uint32_t resident = (uint32_t)num_sms * 2u;  // __launch_bounds__(.., 2)
     const uint32_t sync_grid = sync_blocks < resident ? sync_blocks : resident;
+    const uint32_t check_grid = (n_regions + 31u) / 32u;  // 8 warps x 4 regions per CTA
+    // one repair round: list the regions with a wrong entry, walk those again from their neighbours' exits
+    auto repair = [&](int round) -> cudaError_t {
+        cudaError_t e = cudaMemsetAsync(a.work_count, 0, 4, stream);
+        if (e != cudaSuccess) return e;
+        region_check_kernel<<<check_grid, 256, 0, stream>>>(a, n_regions);
+        region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, round);
+        if (launches) *launches += 2;
+        return cudaSuccess;
+    };
     region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 0);
-    region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 1);
+    if (launches) *launches += 1;
+    if ((err = repair(1)) != cudaSuccess) return err;
     if ((err = cudaMemsetAsync(a.changed, 0, 8, stream)) != cudaSuccess) return err;  // changed and max_sum
-    if (launches) *launches += 2;
     uint32_t rounds = 2;
     for (;;) {
         const uint32_t n_groups = (n_regions + kGroupRegions - 1) / kGroupRegions;
@@ -1409,13 +1431,15 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
             fprintf(stderr, "[lanes] regions=%u chunks=%u max_sum=%u rounds=%u changed=%u\n", n_regions, a.n_chunks,
                     *reinterpret_cast<const uint32_t *>(h_hdr + 20), rounds, *h_changed);
         if (*h_changed == 0) break;  // every entry was the true one: what the write walk produced stands
-        // entries still moving: fixpoint rounds, four per host visit (the flag is cleared before the last of them)
+        // entries still moving: fixpoint rounds, four per host visit; a check that lists nothing is the proof
         for (;;) {
-            for (int i = 0; i < 3; ++i) region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + i);
-            if ((err = cudaMemsetAsync(a.changed, 0, 8, stream)) != cudaSuccess) return err;
-            region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, (int)rounds + 3);
+            for (int i = 0; i < 4; ++i)
+                if ((err = repair((int)rounds + i)) != cudaSuccess) return err;
             rounds += 4;
-            if (launches) *launches += 4;
+            if ((err = cudaMemsetAsync(a.changed, 0, 8, stream)) != cudaSuccess) return err;
+            if ((err = cudaMemsetAsync(a.work_count, 0, 4, stream)) != cudaSuccess) return err;
+            region_check_kernel<<<check_grid, 256, 0, stream>>>(a, n_regions);
+            if (launches) *launches += 1;
             if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
             if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
             if (getenv("ET_DEBUG_LANES")) fprintf(stderr, "[lanes] repair rounds=%u changed=%u\n", rounds, *h_changed);
@@ -1471,6 +1495,8 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.exit_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 6);
     a.mid = reinterpret_cast<uint32_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 8);
     a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 12 + 63) & ~(size_t)63));
+    a.work = reinterpret_cast<uint32_t *>(a.group_prefix + (nb + 1023) / 1024 + 1);
+    a.work_count = reinterpret_cast<uint32_t *>(p + 32);
     a.out = d_out;
     a.max_symbols = max_symbols;
 
