@@ -3,7 +3,8 @@
     python tools/profile_summary.py <round-tag> <launches.csv> <raw.csv> [workload]
 
   launches.csv : ncu --metrics gpu__time_duration.sum --csv --log-file ... (every launch, cold cache, serialised)
-  raw.csv      : ncu -i prof.ncu-rep --page raw --csv                      (one --set full capture per kernel)
+  raw.csv      : ncu -i prof.ncu-rep --page raw --csv                      (one --set full capture per kernel;
+                 several files separated by commas are merged)
 Writes profiles/<tag>_launches.md, profiles/<tag>_kernels.md and profiles/traffic.json (dram bytes per launch,
 read by bench.py for roofline.traffic).
 """
@@ -53,8 +54,15 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
     f.write(f"| **total** | {len(step)} | {tot:.1f} | 100% |\n")
 
 # ---- full captures
-rows = list(csv.reader(open(raw_csv)))
-hdr, units, data = rows[0], rows[1], rows[2:]
+# raw_csv may be several files separated by commas (captures of different kernels of the same step): each row keeps
+# the units of its own file
+hdr, data = None, []
+for path in raw_csv.split(","):
+    rows = list(csv.reader(open(path)))
+    if hdr is None:
+        hdr = rows[0]
+    assert rows[0] == hdr, "captures were exported with different metric sets"
+    data += [(r, rows[1]) for r in rows[2:]]
 col = {h: i for i, h in enumerate(hdr)}
 keys = [
     ("gpu__time_duration.sum", "duration"),
@@ -71,6 +79,10 @@ keys = [
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
     ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data pipe busy %"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe busy % (of active cycles)"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe busy % (of active cycles)"),
+    ("sm__cycles_active.avg", "SM active cycles (avg)"),
+    ("sm__cycles_elapsed.max", "SM elapsed cycles (max)"),
     ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
 ]
 stalls = [h for h in hdr if "issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
@@ -82,7 +94,7 @@ except Exception:
 traffic.pop(workload, None)  # first capture of a kernel wins within one run (later launches of it are check rounds)
 with open(os.path.join(ROOT, "profiles", f"{tag}_kernels.md"), "w") as f:
     f.write(f"# {tag}: `ncu --set full --clock-control none` per kernel ({workload})\n\n")
-    for r in data:
+    for r, units in data:
         name = short(r[col["Kernel Name"]])
         f.write(f"## {name}\n\n| metric | value |\n|---|---|\n")
         for k, label in keys:
