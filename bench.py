@@ -334,6 +334,9 @@ def run_ours(args, rank, world):
     if kind == "file":
         data = host_sample(kind, n_total)[plan.lo:plan.hi]
         inp[:n].copy_(torch.from_numpy(data.copy()))
+    elif kind == "fib32" and world == 1:
+        # exact counts, shuffled: the Huffman tree is a chain of depth 32 — i.i.d. sampling is not
+        inp[:n].copy_(synth.shuffled_dev(synth.fibonacci_counts(n, 32)))
     else:
         codec.synth_dev(inp.data_ptr(), n, synth.SEED, plan.lo, thr)
     arm = OneGpu(codec, n, stream) if world == 1 else ManyGpus(codec, plan, dist, stream)

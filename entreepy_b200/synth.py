@@ -62,3 +62,33 @@ def fibonacci_weights(depth=32):
     while len(f) < depth + 1:
         f.append(f[-1] + f[-2])
     return f[: depth + 1] + [0] * (256 - depth - 1)
+
+
+def fibonacci_counts(n, depth=32):
+    """Exact symbol counts for the maximum-depth configuration: depth+1 symbols whose counts are
+    F(1)..F(depth+1) times the largest factor that fits n, the remainder added to the most frequent one.
+    Scaling keeps the tree a chain, so the longest code has `depth` bits — i.i.d. sampling from the same
+    weights does not (the rarest symbols come out with the wrong ratios, or not at all)."""
+    f = [1, 1]
+    while len(f) < depth + 1:
+        f.append(f[-1] + f[-2])
+    f = f[: depth + 1]
+    k = n // sum(f)
+    if k < 1:
+        raise ValueError("n too small for a chain of this depth")
+    counts = [k * x for x in f] + [0] * (256 - depth - 1)
+    counts[depth] += n - k * sum(f)
+    return counts
+
+
+def shuffled_dev(counts, seed=SEED, device="cuda"):
+    """uint8 CUDA tensor with exactly counts[s] copies of every symbol s, in a seeded random order (torch's
+    generator: reproducible on the same device type, not the CPU twin of anything)."""
+    import torch
+
+    c = torch.tensor(list(counts), dtype=torch.int64, device=device)
+    runs = torch.repeat_interleave(torch.arange(256, dtype=torch.uint8, device=device), c)
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed) & 0x7FFFFFFF)
+    perm = torch.randperm(runs.numel(), generator=g, device=device)
+    return runs[perm]
