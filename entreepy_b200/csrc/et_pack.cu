@@ -180,8 +180,10 @@ __device__ __forceinline__ bool region_is_interior(const PackArgs &a, uint32_t r
 
 // (acc << len) | code on a 64-bit accumulator, len 0..32.  pos is the absolute BIT address of the next bit
 // in shared memory (byte address x 8 + bit, MSB first inside a word); when it crosses a word boundary the
-// 32 bits before the boundary are complete and are ORed into the image under a predicate — no branch, the
-// lanes of a warp stay together whatever their code lengths are.
+// 32 bits before the boundary are complete and are STORED under a predicate — no branch, the lanes of a warp
+// stay together whatever their code lengths are.  A lane's first such word also covers the last bits of the
+// lanes before it (zeros here): those lanes OR their unfinished last word in after the warp has met
+// (pack_runs_kernel), so every word of the image is written exactly once and ORed at most a few times.
 struct BitAcc {
     uint32_t hi, lo, pos;
 };
@@ -189,11 +191,8 @@ __device__ __forceinline__ void push_acc(BitAcc &b, uint32_t code, uint32_t len)
     b.hi = __funnelshift_lc(b.lo, b.hi, len);
     b.lo = __funnelshift_lc(0u, b.lo, len) | code;
     const uint32_t p2 = b.pos + len;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %0, 32;\n\tsetp.ne.u32 p, t, 0;\n\t@p red.shared.or.b32 [%1], %2;\n\t}" ::"r"(
-            b.pos ^ p2),
-        "r"(((p2 >> 3) & ~3u) - 4u), "r"(__funnelshift_r(b.lo, b.hi, p2))
-        : "memory");
+    if ((b.pos ^ p2) & 32u)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(((p2 >> 3) & ~3u) - 4u), "r"(__funnelshift_r(b.lo, b.hi, p2)) : "memory");
     b.pos = p2;
 }
 
@@ -332,9 +331,12 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
         const unsigned long long bit_end = bit_begin + region_bits;
         if (lane == 0) a.tile_state[r] = bit_end;  // for the seam fix-up
 
-        // ---- assemble at region-relative positions (words hold stream bits MSB-first; every store is an OR:
-        // the first and last word of a lane are shared with its neighbours)
+        // ---- assemble at region-relative positions (words hold stream bits MSB-first)
         {
+            // the word in which the region ends is only ever ORed into (or not touched at all), and the byte in which
+            // it ends may reach into the word after it: both start from zero
+            if (lane < 2) stage[kStageGuard + (region_bits >> 5) + lane] = 0;
+            __syncwarp();
             BitAcc acc;
             acc.hi = acc.lo = 0;
             acc.pos = (uint32_t)__cvta_generic_to_shared(stage + kStageGuard) * 8u + my_off;
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
                     }
                 }
             }
+            __syncwarp();  // every whole word is in place
             if (acc.pos & 31u) atomicOr(stage + kStageGuard + ((my_off + my_bits) >> 5), acc.lo << (32u - (acc.pos & 31u)));
         }
         __syncwarp();  // image complete
@@ -428,8 +431,6 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
             }
         }
         __syncwarp();  // everyone has read the image
-        for (uint32_t i = lane; i < ((region_bits + 31u) >> 5) + 1u; i += 32) stage[kStageGuard + i] = 0;
-        __syncwarp();
         if (r_next >= a.n_regions) break;
         r = r_next;
     }

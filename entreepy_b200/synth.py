@@ -91,4 +91,6 @@ def shuffled_dev(counts, seed=SEED, device="cuda"):
     g = torch.Generator(device=device)
     g.manual_seed(int(seed) & 0x7FFFFFFF)
     perm = torch.randperm(runs.numel(), generator=g, device=device)
-    return runs[perm]
+    out = runs[perm]
+    torch.cuda.synchronize()  # callers hand the pointer to the codec, which works on its own stream
+    return out
