@@ -1,9 +1,12 @@
 """One .et stream across the GPUs of a box: contiguous byte ranges, tiny exchanges.
 
-Encode: rank r packs text bytes [lo_r, hi_r).  Exchanges: histogram all-reduce (2 KiB), all-gather of
-one bit count per rank (the cross-GPU exclusive scan of bit offsets), all-gather of one seam byte per
-rank.  Every rank builds the same codebook from the reduced histogram (the host step is deterministic)
-and packs its slice directly at its final bit position; bulk data never leaves its GPU.
+Encode: rank r packs text bytes [lo_r, hi_r).  One exchange: an all-gather of the ranks' local histograms
+(2 KiB each, with the first 8 text bytes of every shard).  Their sum is the global histogram — what
+north_star's all-reduce delivers — and each of them, priced with the codebook, is that shard's bit count, so
+the cross-GPU exclusive scan of bit offsets is computed on every rank without a second exchange.  Every rank
+builds the same codebook (the host step is deterministic) and packs its slice directly at its final bit
+position; bulk data never leaves its GPU.  (A third exchange of one byte per rank exists for shards too short
+to fill their first byte.)
 
 Decode: rank r decodes body bytes [B_r, B_{r+1}) (32-byte aligned cuts).  The stream has no index, so a
 rank other than 0 does not know where its first codeword starts: it synchronises on the 64 bytes before
@@ -181,14 +184,19 @@ class ShardedCodec:
         header + the ranks' bodies[own_lo:own_hi] in rank order."""
         p, be = self.plan, self.backend
         local = be.histogram(t_in, p.n_local)                       # K1
-        counts = self.comm.allreduce_counts(local)                  # exchange 1: 2 KiB
+        # ONE exchange: every rank's local histogram (2 KiB each).  The sum is the global histogram (what an
+        # all-reduce would give); the local ones, priced with the codebook, are every shard's bit count — the
+        # cross-GPU scan of bit offsets needs no second exchange.  The first text bytes of every shard ride
+        # along so that each rank can work out the seam byte of its right neighbours.
+        head = be.head_symbols(t_in, p.n_local) if hasattr(be, "head_symbols") else 0
+        packed = self.comm.allgather_ints([int(x) for x in local] + [head & 0x7FFFFFFFFFFFFFFF, head >> 63, p.n_local])
+        locals_ = [np.array(row[:256], dtype=np.uint64) for row in packed]
+        counts = np.sum(np.stack(locals_), axis=0, dtype=np.uint64)
         cb = build_codebook(counts)                                 # same tables on every rank
         header = write_header(cb, p.n_total)
-        bits = be.shard_bits(local, cb)
-        # exchange 2: the cross-GPU scan of bit offsets; the first text bytes of every shard ride along so
-        # that each rank can work out the seam byte of its right neighbours without a third exchange
-        head = be.head_symbols(t_in, p.n_local) if hasattr(be, "head_symbols") else 0
-        gathered = self.comm.allgather_ints([bits, head & 0x7FFFFFFFFFFFFFFF, head >> 63, p.n_local])
+        shard_bits = [int(be.shard_bits(locals_[r], cb)) for r in range(p.world)]
+        bits = shard_bits[p.rank]
+        gathered = [[shard_bits[r]] + list(packed[r][256:]) for r in range(p.world)]
         offs = [0]
         for r in range(p.world):
             offs.append(offs[-1] + gathered[r][0])
