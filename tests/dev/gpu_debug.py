@@ -5,7 +5,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import entreepy_b200 as et  # noqa: E402
 from entreepy_b200 import synth  # noqa: E402
