@@ -7,7 +7,9 @@
  *
  * Source of truth: /root/reference/src/{encode,decode,queue}.zig (Zig 0.12, cannot be
  * compiled in this image — no Zig toolchain).  Each function cites the lines it restates.
- * Pinning: the reference ships NO golden .et vectors (test.zig only checks round trips);
+ * PARITY UNPINNED against the reference binary: it cannot be built or run here and it ships no
+ * golden .et vectors, so no byte of .et output of the real executable has been observed.
+ * Pinning that does exist: the reference ships NO golden .et vectors (test.zig only checks round trips);
  * this oracle is pinned against (a) README.md:51 "477 bytes -> 374 bytes", (b) the three
  * round-trip fixtures of test.zig:35-72, (c) the hand-traced res/test.txt bytes and the
  * sha256 values in SURVEY.md §8c, which came from an independent restatement, and (d)
