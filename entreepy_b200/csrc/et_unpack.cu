@@ -1,30 +1,34 @@
 // K3-K5 — parallel Huffman decode of an .et body (replaces decode.zig:143-203).
 //
 // The stream carries no block index, so nobody knows where a codeword starts.  The body is
-// cut into chunks (256 B by default), one THREAD per chunk, and the codeword boundary at
-// which each chunk starts is found by self-synchronisation plus a fixpoint check:
-//   sync 0   every chunk starts decoding one 16-byte piece BEFORE its first bit, from a guess.
+// cut into chunks and the codeword boundary at which each chunk starts is found by
+// self-synchronisation plus a fixpoint check:
+//   sync 0   every chunk starts decoding a few words BEFORE its first bit, from a guess.
 //            Huffman codes re-synchronise after a few symbols, so by the time the walk
 //            enters the chunk it is almost always on a true boundary.  It records where it
 //            entered, how many symbols begin in the chunk and where its last codeword ends.
 //   sync r   a chunk whose recorded entry differs from its left neighbour's recorded end
-//            decodes again from there.  A round in which nothing changed proves, by
+//            decodes again from there.  A pass in which nothing differed proves, by
 //            induction from chunk 0 (true start), that every entry is the true one.  Text
-//            needs one (empty) check round; codes with nearly equal lengths (uniform bytes:
-//            7/8-bit codes) need a few; the worst case is one round per chunk and still ends.
-//   scan     block sums of the symbol counts, exclusive scan of the block sums (64-bit);
-//   write    every chunk decodes once more from its proven entry; symbols go through a
-//            private shared-memory row and leave as aligned 16-byte stores.
-// Nothing here bets on luck: the guess only decides how many chunks the check rounds redo.
+//            needs one repair round; codes with nearly equal lengths (uniform bytes:
+//            7/8-bit codes) need tens; the worst case is one round per chunk and still ends.
+//   scan     exclusive scan of the symbol counts (64-bit);
+//   write    every chunk decodes once more from its proven entry.
+// Nothing here bets on luck: the guess only decides how many chunks the repair rounds redo.
 //
-// The kernels are instruction-bound (ncu: profiles/), so the walkers are written for
-// instruction count.  A thread streams its chunk through registers 16 bytes at a time; bit
-// position and symbol count (or output address) share ONE register (bits 0-8 / 9+); every
-// table entry is a pre-packed add for that register; loop tests are single bit tests because
-// the position is kept relative to the 32-bit word being decoded.  Because a thread owns a
-// long contiguous run there is no per-subsequence speculation: two table walks per symbol
-// in total (count, write).  Anything unusual (ragged ends of the stream, output clipped by
-// body_len) takes the generic walker, one symbol at a time with every check.
+// Two implementations of that protocol live in this file:
+//   * the LANE-INTERLEAVED decoder (second half of the file) for long streams of codes that
+//     re-synchronise quickly — the path the benchmarks run: chunks of 33 words, a warp per
+//     region of 32 chunks staged in shared memory, flat two-lookup walks, the text of a
+//     region assembled in shared memory and stored as whole 16-byte vectors;
+//   * the per-THREAD chunk kernels (first half) for short streams and for codes whose lengths
+//     differ by at most 2 bits: one thread per chunk of 32..4096 bytes, stream words in
+//     registers 16 bytes at a time, bit position and symbol count (or output address) in ONE
+//     register, table entries that are pre-packed adds for it.  Anything unusual there (ragged
+//     ends of the stream, output clipped by body_len) takes the generic walker, one symbol at
+//     a time with every check.
+// All of them are bound by instruction issue and the integer pipe, not by HBM (ncu: profiles/),
+// so the walkers are written for instruction count.
 #include <cstdio>
 #include <cstdlib>
 
@@ -142,7 +146,7 @@ __device__ __forceinline__ uint32_t long_code_add(uint32_t hi, uint32_t lo, uint
     return 1u;
 }
 
-// ------------------------------------------------------------------ fast walkers
+// ------------------------------------------------------------------ fast walkers (per-thread chunk kernels)
 // Packed state c: bits 0-8 position relative to the 32-bit word being decoded (bit 8 set =
 // marker entry hit), bits 9+ symbol count (count walk) or staging address (write walk).
 //
