@@ -325,6 +325,11 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
         const uint32_t my_bits = a.run_bits[(size_t)r * 32 + lane];
         const unsigned long long bit_begin = a.group_prefix[r >> a.group_shift] + a.tile_bits[r];
         const uint32_t r_next = r + stride;
+        if (r_next < a.n_regions) {  // the next region's text and run totals on their way into L2 (no registers held)
+            const uint8_t *nx = lane < 16 ? a.in_aligned + (uint64_t)r_next * kRegionSyms + lane * 128u
+                                          : reinterpret_cast<const uint8_t *>(a.run_bits + (size_t)r_next * 32);
+            if (lane <= 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        }
         const uint32_t incl = warp_inclusive_scan(my_bits, lane);
         const uint32_t region_bits = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t my_off = incl - my_bits;

@@ -1388,18 +1388,23 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
 // look at the scratch header after the scan: the largest region sizes the text stage of a warp.
 static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, const void *d_header, uint8_t *h_hdr, cudaStream_t stream,
                                        int *launches, uint32_t *rounds_out) {
-    static int max_smem = 0, num_sms = 0;
+    // per device: the shared-memory opt-in of the two big kernels is a property of the function ON that device
+    static int smem_of[64] = {0}, sms_of[64] = {0};
     cudaError_t err;
-    if (!max_smem) {
-        int dev = 0;
-        if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
-        if ((err = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
-        if ((err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
-        if ((err = cudaFuncSetAttribute(region_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess)
+    int dev = 0;
+    if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!smem_of[dev]) {
+        int smem = 0;
+        if ((err = cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+        if ((err = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
+        if ((err = cudaFuncSetAttribute(region_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
             return err;
         if ((err = cudaFuncSetAttribute(region_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmem)) != cudaSuccess)
             return err;
+        smem_of[dev] = smem;
     }
+    const int max_smem = smem_of[dev], num_sms = sms_of[dev];
     const uint32_t *h_changed = reinterpret_cast<const uint32_t *>(h_hdr + 16);
     const uint32_t sync_blocks = (n_regions + kSyncWarps - 1) / kSyncWarps;
     const uint32_t resident = (uint32_t)num_sms * 2u;  // __launch_bounds__(.., 2)
