@@ -25,7 +25,9 @@ struct PackGeometry {
 };
 PackGeometry pack_geometry(const void *d_in, size_t n);
 
-// Device scratch the pack kernels need for `num_tiles` tiles.
+// Device scratch the pack kernels need for `num_tiles` tiles (4096 symbols each).  The wide kernel (codes of
+// 33..64 bits) works on those tiles; the lane-run path (codes <= 32 bits) carves the same block for its regions
+// of 2048 symbols (two per tile) and its u16 run totals: pack_scratch_bytes() covers both.
 struct PackScratch {
     unsigned long long *tile_state;   // [num_tiles] last bit + 1 of each tile (wide kernel: look-back descriptors)
     unsigned long long *group_prefix; // [ceil(num_tiles / 256)] bits before each group of tiles
