@@ -97,10 +97,26 @@ class Comm:
             return [list(values)]
         import torch
 
-        t = torch.tensor(list(values), dtype=torch.int64, device=self.device)
-        out = torch.empty(self.world * len(values), dtype=torch.int64, device=self.device)
-        self.dist.all_gather_into_tensor(out, t)
-        return out.cpu().view(self.world, len(values)).tolist()
+        k = len(values)
+        if self.device.type != "cuda":
+            t = torch.tensor(list(values), dtype=torch.int64, device=self.device)
+            out = torch.empty(self.world * k, dtype=torch.int64, device=self.device)
+            self.dist.all_gather_into_tensor(out, t)
+            return out.cpu().view(self.world, k).tolist()
+        # GPU: page-locked staging and device buffers are allocated once; the exchanges are a few hundred bytes
+        # and their cost is launch and copy latency, not bandwidth
+        if getattr(self, "_cap", 0) < k:
+            self._cap = max(512, k)
+            self._h_send = torch.empty(self._cap, dtype=torch.int64).pin_memory()
+            self._h_recv = torch.empty(self._cap * self.world, dtype=torch.int64).pin_memory()
+            self._d_send = torch.empty(self._cap, dtype=torch.int64, device=self.device)
+            self._d_recv = torch.empty(self._cap * self.world, dtype=torch.int64, device=self.device)
+        self._h_send.numpy()[:k] = np.asarray(values, dtype=np.int64)
+        self._d_send[:k].copy_(self._h_send[:k], non_blocking=True)
+        self.dist.all_gather_into_tensor(self._d_recv[: self.world * k], self._d_send[:k])
+        self._h_recv[: self.world * k].copy_(self._d_recv[: self.world * k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._h_recv.numpy()[: self.world * k].reshape(self.world, k).tolist()
 
     def all_to_all_bytes(self, send, send_splits, recv_splits):
         """Uneven all-to-all of byte ranges (point-to-point pairs: works on nccl and gloo alike)."""
@@ -156,6 +172,25 @@ class GpuBackend:
         k = min(n, 8)
         return int.from_bytes(bytes(t_in[:k].cpu().numpy()), "little") if k else 0
 
+    def head_symbols_begin(self, t_in, n):
+        """Starts the copy of the first text bytes into page-locked memory; head_symbols_end() reads them after
+        the next synchronisation of the stream (the histogram's), so the copy costs no round trip of its own."""
+        import torch
+
+        k = min(n, 8)
+        if not hasattr(self, "_head"):
+            self._head = torch.zeros(8, dtype=torch.uint8).pin_memory()
+            self._head_done = torch.cuda.Event()
+        if k:
+            self._head[:k].copy_(t_in[:k], non_blocking=True)
+            self._head_done.record()
+        return k
+
+    def head_symbols_end(self, k):
+        if k:
+            self._head_done.synchronize()  # already signalled when the histogram ran on the same stream
+        return int.from_bytes(bytes(self._head[:k].numpy()), "little") if k else 0
+
 
 def first_output_byte(cb, head, n, phase):
     """First byte a shard writes when packed at bit `phase`: its leading codes behind `phase` zero bits.
@@ -183,12 +218,16 @@ class ShardedCodec:
         what the reference's 7200+n scratch bound guarantees).  Returns EncodeResult; the .et file is
         header + the ranks' bodies[own_lo:own_hi] in rank order."""
         p, be = self.plan, self.backend
-        local = be.histogram(t_in, p.n_local)                       # K1
+        pending = be.head_symbols_begin(t_in, p.n_local) if hasattr(be, "head_symbols_begin") else None
+        local = be.histogram(t_in, p.n_local)                       # K1 (synchronises the stream)
         # ONE exchange: every rank's local histogram (2 KiB each).  The sum is the global histogram (what an
         # all-reduce would give); the local ones, priced with the codebook, are every shard's bit count — the
         # cross-GPU scan of bit offsets needs no second exchange.  The first text bytes of every shard ride
         # along so that each rank can work out the seam byte of its right neighbours.
-        head = be.head_symbols(t_in, p.n_local) if hasattr(be, "head_symbols") else 0
+        if pending is not None:
+            head = be.head_symbols_end(pending)
+        else:
+            head = be.head_symbols(t_in, p.n_local) if hasattr(be, "head_symbols") else 0
         packed = self.comm.allgather_ints([int(x) for x in local] + [head & 0x7FFFFFFFFFFFFFFF, head >> 63, p.n_local])
         locals_ = [np.array(row[:256], dtype=np.uint64) for row in packed]
         counts = np.sum(np.stack(locals_), axis=0, dtype=np.uint64)
