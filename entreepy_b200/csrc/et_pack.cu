@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kPackThreads) run_bits_kernel(const PackArgs a
     const uint32_t n_slabs = (a.n_regions + 1) / 2, group_slabs = a.group_tiles / 2;
     const uint32_t s_lo = blockIdx.x * group_slabs, s_hi = min(s_lo + group_slabs, n_slabs);
     const uint32_t slab_int_lo = (a.interior_lo + 1) / 2, slab_int_hi = a.interior_hi / 2;  // slabs wholly inside the input
-    uint32_t run = 0;  // bits of the group so far (same value in every thread)
+    uint32_t run = 0;  // bits of the group so far (kept by warp 0)
     constexpr int kBatch = 4;  // slabs per iteration: four independent 16-byte loads in flight per thread
     for (uint32_t s0 = s_lo; s0 < s_hi; s0 += kBatch) {
         uint4 raw[kBatch];
@@ -252,8 +252,7 @@ __global__ void __launch_bounds__(kPackThreads) run_bits_kernel(const PackArgs a
             bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], 1);
             bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], 2);
             if ((lane & 3u) == 0 && s0 + b < s_hi) a.run_bits[(size_t)(s0 + b) * 64 + (tid >> 2)] = (uint16_t)bits[b];
-#pragma unroll
-            for (int o = 16; o > 2; o >>= 1) bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], o);
+            bits[b] = __reduce_add_sync(0xffffffffu, (lane & 3u) == 0 ? bits[b] : 0u);  // one REDUX instead of three shuffles
         }
         uint32_t *ws = warp_sum[((s0 - s_lo) / kBatch) & 1];  // double-buffered: one barrier per batch
         if (lane == 0) {
@@ -261,14 +260,16 @@ __global__ void __launch_bounds__(kPackThreads) run_bits_kernel(const PackArgs a
             for (int b = 0; b < kBatch; ++b) ws[b * kWarps + warp] = bits[b];
         }
         __syncthreads();
+        if (warp == 0) {  // only the thread that writes the prefixes needs the running total
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
+            for (int b = 0; b < kBatch; ++b) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {  // the two regions of the slab
-                const uint32_t r = 2 * (s0 + b) + h;
-                if (tid == 0 && s0 + b < s_hi && r < a.n_regions) a.tile_bits[r] = run;
+                for (int h = 0; h < 2; ++h) {  // the two regions of the slab
+                    const uint32_t r = 2 * (s0 + b) + h;
+                    if (tid == 0 && s0 + b < s_hi && r < a.n_regions) a.tile_bits[r] = run;
 #pragma unroll
-                for (int q = 0; q < kWarps / 2; ++q) run += ws[b * kWarps + h * (kWarps / 2) + q];
+                    for (int q = 0; q < kWarps / 2; ++q) run += ws[b * kWarps + h * (kWarps / 2) + q];
+                }
             }
         }
     }
