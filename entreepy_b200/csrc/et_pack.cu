@@ -410,17 +410,34 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
                 if (!has_head) a.seam_head[r] = 0;
                 if (!has_tail) a.seam_tail[r] = 0;
             }
-            // frame word f holds region bits [32f - shift, 32f - shift + 32)
-            const uint32_t rot = (32u - (shift & 31u)) & 31u;
-            const int back = (int)((shift + 31u) >> 5);  // image words the frame starts before the region
+            // frame word f holds region bits [32f - shift, 32f - shift + 32): image word f - ws shifted right by bs
+            // bits, its top bits coming from the word before.  Two aligned 16-byte shared loads per chunk (the four
+            // image words of the chunk and the four before them: conflict-free), then a warp-uniform choice of which
+            // of the eight words feed which frame word.
+            const uint32_t bs = shift & 31u, ws = shift >> 5;
             for (uint32_t c = lane; c < n_chunks; c += 32) {
-                const uint32_t *src = stage + kStageGuard + (int)(4 * c) - back;
-                const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3], w4 = src[4];
-                uint4 v;
-                v.x = bswap32(__funnelshift_l(w1, w0, rot));
-                v.y = bswap32(__funnelshift_l(w2, w1, rot));
-                v.z = bswap32(__funnelshift_l(w3, w2, rot));
-                v.w = bswap32(__funnelshift_l(w4, w3, rot));
+                const uint4 *src = reinterpret_cast<const uint4 *>(stage + kStageGuard) + c;
+                const uint4 p = src[-1], q = src[0];
+                uint32_t f0, f1, f2, f3;
+                switch (ws) {
+                    case 0:
+                        f0 = __funnelshift_r(q.x, p.w, bs); f1 = __funnelshift_r(q.y, q.x, bs);
+                        f2 = __funnelshift_r(q.z, q.y, bs); f3 = __funnelshift_r(q.w, q.z, bs);
+                        break;
+                    case 1:
+                        f0 = __funnelshift_r(p.w, p.z, bs); f1 = __funnelshift_r(q.x, p.w, bs);
+                        f2 = __funnelshift_r(q.y, q.x, bs); f3 = __funnelshift_r(q.z, q.y, bs);
+                        break;
+                    case 2:
+                        f0 = __funnelshift_r(p.z, p.y, bs); f1 = __funnelshift_r(p.w, p.z, bs);
+                        f2 = __funnelshift_r(q.x, p.w, bs); f3 = __funnelshift_r(q.y, q.x, bs);
+                        break;
+                    default:
+                        f0 = __funnelshift_r(p.y, p.x, bs); f1 = __funnelshift_r(p.z, p.y, bs);
+                        f2 = __funnelshift_r(p.w, p.z, bs); f3 = __funnelshift_r(q.x, p.w, bs);
+                        break;
+                }
+                const uint4 v = make_uint4(bswap32(f0), bswap32(f1), bswap32(f2), bswap32(f3));
                 const uint32_t k0 = c * 16;
                 if (k0 >= s_lo && k0 + 16 <= s_hi) {
                     st_stream_v4(gbase + k0, v);
