@@ -95,14 +95,20 @@ class Comm:
         """values: list of python ints (non-negative, < 2^63) -> [world][len(values)]."""
         if self.world == 1:
             return [list(values)]
+        return self.allgather_array(np.asarray(values, dtype=np.int64)).tolist()
+
+    def allgather_array(self, values):
+        """values: int64[k] (non-negative) -> int64[world, k]."""
         import torch
 
-        k = len(values)
+        k = int(values.size)
+        if self.world == 1:
+            return values.reshape(1, k).copy()
         if self.device.type != "cuda":
-            t = torch.tensor(list(values), dtype=torch.int64, device=self.device)
+            t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.int64)).to(self.device)
             out = torch.empty(self.world * k, dtype=torch.int64, device=self.device)
             self.dist.all_gather_into_tensor(out, t)
-            return out.cpu().view(self.world, k).tolist()
+            return out.cpu().view(self.world, k).numpy().copy()
         # GPU: page-locked staging and device buffers are allocated once; the exchanges are a few hundred bytes
         # and their cost is launch and copy latency, not bandwidth
         if getattr(self, "_cap", 0) < k:
@@ -111,12 +117,12 @@ class Comm:
             self._h_recv = torch.empty(self._cap * self.world, dtype=torch.int64).pin_memory()
             self._d_send = torch.empty(self._cap, dtype=torch.int64, device=self.device)
             self._d_recv = torch.empty(self._cap * self.world, dtype=torch.int64, device=self.device)
-        self._h_send.numpy()[:k] = np.asarray(values, dtype=np.int64)
+        self._h_send.numpy()[:k] = values
         self._d_send[:k].copy_(self._h_send[:k], non_blocking=True)
         self.dist.all_gather_into_tensor(self._d_recv[: self.world * k], self._d_send[:k])
         self._h_recv[: self.world * k].copy_(self._d_recv[: self.world * k], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self._h_recv.numpy()[: self.world * k].reshape(self.world, k).tolist()
+        return self._h_recv.numpy()[: self.world * k].reshape(self.world, k).copy()
 
     def all_to_all_bytes(self, send, send_splits, recv_splits):
         """Uneven all-to-all of byte ranges (point-to-point pairs: works on nccl and gloo alike)."""
@@ -228,14 +234,20 @@ class ShardedCodec:
             head = be.head_symbols_end(pending)
         else:
             head = be.head_symbols(t_in, p.n_local) if hasattr(be, "head_symbols") else 0
-        packed = self.comm.allgather_ints([int(x) for x in local] + [head & 0x7FFFFFFFFFFFFFFF, head >> 63, p.n_local])
-        locals_ = [np.array(row[:256], dtype=np.uint64) for row in packed]
-        counts = np.sum(np.stack(locals_), axis=0, dtype=np.uint64)
+        send = np.empty(259, dtype=np.int64)
+        send[:256] = local
+        send[256:] = (head & 0x7FFFFFFFFFFFFFFF, head >> 63, p.n_local)
+        packed = self.comm.allgather_array(send)                    # [world, 259]
+        locals_ = packed[:, :256].astype(np.uint64)
+        counts = locals_.sum(axis=0, dtype=np.uint64)
         cb = build_codebook(counts)                                 # same tables on every rank
         header = write_header(cb, p.n_total)
-        shard_bits = [int(be.shard_bits(locals_[r], cb)) for r in range(p.world)]
+        # bits of every shard = its local counts priced with the code lengths (what et_shard_bits computes)
+        lengths = np.frombuffer(cb, dtype=np.dtype([("data", "<u4"), ("length", "u1"), ("pad", "V3")]), count=256)["length"]
+        shard_bits = [int(x) for x in (locals_ * lengths.astype(np.uint64)).sum(axis=1, dtype=np.uint64)]
         bits = shard_bits[p.rank]
-        gathered = [[shard_bits[r]] + list(packed[r][256:]) for r in range(p.world)]
+        tails = packed[:, 256:].tolist()
+        gathered = [[shard_bits[r]] + tails[r] for r in range(p.world)]
         offs = [0]
         for r in range(p.world):
             offs.append(offs[-1] + gathered[r][0])

@@ -50,4 +50,12 @@ for it in range(6):
 if rank == 0:
     print("encode ms", tenc / 5 * 1e3, "decode ms", tdec / 5 * 1e3)
     for k, v in sorted(T.items(), key=lambda x: -x[1]): print(f"  {k:16s} {v / 5 * 1e3:8.3f} ms/step")
+    print("cpus usable by a rank:", len(os.sched_getaffinity(0)), "of", os.cpu_count())
+# every rank: its own phase times (skew shows up as waiting inside the exchanges)
+line = f"rank {rank}: enc {tenc / 5 * 1e3:.3f} dec {tdec / 5 * 1e3:.3f} | " + " ".join(
+    f"{k}={v / 5 * 1e3:.3f}" for k, v in sorted(T.items()) if k in ("histogram", "pack_shard", "unpack_shard", "allgather_ints"))
+for r in range(world):
+    dist.barrier()
+    if r == rank:
+        print(line, flush=True)
 dist.destroy_process_group()
