@@ -133,3 +133,20 @@ def test_synth_generator_is_deterministic(manifest):
     assert np.array_equal(a, b)
     assert set(np.unique(a)) <= {s for s, c in enumerate(manifest["midsummer_histogram"]) if c}
     assert synth.splitmix64(np.uint64(0)) == np.uint64(0xE220A8397B1DCDAF)  # published splitmix64 vector
+
+
+def test_fibonacci_counts_give_the_deepest_faithful_tree():
+    # exact Fibonacci counts scaled to 256 MiB make a chain of depth 32 — the deepest codes the
+    # reference represents faithfully; the host codebook and the oracle agree on every code of it
+    from entreepy_b200 import synth
+
+    counts = np.array(synth.fibonacci_counts(1 << 28, 32), dtype=np.uint64)
+    assert int(counts.sum()) == 1 << 28 and int((counts > 0).sum()) == 33
+    o_code, o_len = oracle.build_dictionary(counts)
+    assert int(o_len.max()) == 32 and sorted(int(x) for x in o_len[o_len > 0]) == [1] + list(range(2, 33)) + [32]
+    cb = et.build_codebook(counts)
+    assert [cb.code[s].length for s in range(256)] == [int(x) for x in o_len]
+    assert [cb.code[s].data for s in range(256)] == [int(x) for x in o_code]
+    # i.i.d. sampling from the same weights does not reach that depth (why the bench uses exact counts)
+    sample = synth.generate(1 << 20, synth.thresholds_from_weights(synth.fibonacci_weights(32)))
+    assert int(oracle.build_dictionary(oracle.histogram(sample))[1].max()) < 32
