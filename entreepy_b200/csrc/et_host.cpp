@@ -303,22 +303,7 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
             t->clut[idx] = kLutMarker | (kLutMarker << 16);
             t->wlut[idx] = (stuck_node & 0xFFFFu) | (kLutMarker << 16);
             if (stuck_node != kChildNone && t->n_slots < kMaxSubTables) {  // second level: the next 8 bits
-                const uint32_t slot = t->n_slots++;
-                t->slot_of[idx] = (uint16_t)slot;
-                for (uint32_t nxt = 0; nxt < (1u << kSubBits); ++nxt) {
-                    uint32_t node = stuck_node;
-                    uint16_t e = 0;
-                    for (uint32_t k = 0; k < kSubBits; ++k) {
-                        const uint32_t c = kid[node][(nxt >> (kSubBits - 1 - k)) & 1u];
-                        if (c == kChildNone) break;
-                        if (c & kChildLeaf) {
-                            e = (uint16_t)((c & 0xFFu) | ((kLutBits + k + 1) << 8));
-                            break;
-                        }
-                        node = c;
-                    }
-                    t->sub[(slot << kSubBits) + nxt] = e;
-                }
+                t->slot_of[idx] = (uint16_t)t->n_slots++;                  // (filled code by code below; memset left it 0)
             }
         } else {
             const uint32_t all = pos | (cnt << 9), one = len0 | (1u << 9);
@@ -326,6 +311,17 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
             t->clut[idx] = all | (one << 16);
             t->wlut[idx] = sym0 | (sym1 << 8) | (two << 16);
         }
+    }
+    // second-level tables: a code of kLutBits+1 .. kLutBits+kSubBits bits owns 2^(kLutBits+kSubBits-len) entries of the
+    // table of its first kLutBits bits
+    for (uint32_t e = 0; e < dict.n_entries; ++e) {
+        const unsigned len = dict.length[e];
+        if (len <= (unsigned)kLutBits || len > (unsigned)kLutBits + kSubBits) continue;
+        const uint16_t slot = t->slot_of[(uint32_t)(dict.code[e] >> (len - kLutBits))];
+        if (slot == kNoSlot) continue;
+        const unsigned rest = len - kLutBits;  // bits of the code after the window
+        const uint32_t lo = (uint32_t)(dict.code[e] & ((1u << rest) - 1u)) << (kSubBits - rest), n = 1u << (kSubBits - rest);
+        for (uint32_t k = lo; k < lo + n; ++k) t->sub[((uint32_t)slot << kSubBits) + k] = (uint16_t)(dict.symbol[e] | (len << 8));
     }
     return ET_OK;
 }
