@@ -297,6 +297,88 @@ class ManyGpus:
         return d.n_local, int(self.plan.n_local + self.range.numel()), int(nb + d.n_local)
 
 
+def verify_one(codec, arm, inp, n, got, kind):
+    """decode(encode(x)) == x on one GPU (north_star)."""
+    import torch
+
+    import entreepy_b200 as et
+
+    verified = got == n and bool(torch.equal(arm.dec[:n], inp[:n]))
+    if not verified and kind == "uniform256":
+        # all 256 byte values occur: the reference encoder gives the last symbol in sort order no code
+        # (encode.zig:70, SURVEY §0.2), so the round trip is the text WITHOUT that symbol — by construction
+        counts = codec.histogram_dev(inp.data_ptr(), n)
+        cb = et.build_codebook(counts)
+        dropped = [s for s in range(256) if counts[s] and cb.code[s].length == 0]
+        keep = inp[:n][inp[:n] != dropped[0]] if len(dropped) == 1 else inp[:0]
+        verified = len(dropped) == 1 and got == keep.numel() and bool(torch.equal(arm.dec[:got], keep))
+    return verified
+
+
+def make_input(codec, name, lo=0, n=None, world=1):
+    """The workload's bytes [lo, lo + n) on the device (same bytes as entreepy_b200/synth.py on the CPU)."""
+    import torch
+
+    from entreepy_b200 import synth
+
+    n_total, kind = WORKLOADS[name]
+    n = n_total if n is None else n
+    inp = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    if kind == "file":
+        inp[:n].copy_(torch.from_numpy(host_sample(kind, n_total)[lo:lo + n].copy()))
+    elif kind == "fib32" and world == 1:
+        # exact counts, shuffled (SURVEY §0.4): the Huffman tree is a chain of depth 32 — i.i.d. sampling is not
+        inp[:n].copy_(synth.shuffled_dev(synth.fibonacci_counts(n, 32)))
+    else:
+        codec.synth_dev(inp.data_ptr(), n, synth.SEED, lo, thresholds(kind))
+    torch.cuda.synchronize()
+    return inp
+
+
+OTHER_CONFIGS = ["midsummer", "text-5M", "uniform255", "uniform256", "fib32", "text-4G"]  # BASELINE.json configs 1, 2, 4, 5
+
+
+def run_other_configs(codec, stream, peak, steps=3):
+    """BASELINE.json's other configurations on one GPU, device resident, outside the headline's timed region:
+    encode and decode milliseconds (CUDA events, mean of `steps` after two warm-up steps), fraction of the HBM
+    roofline in algorithmic bytes (2N + C, C + N), fixpoint rounds of the decoder, round trip checked."""
+    import torch
+
+    out = []
+    for name in OTHER_CONFIGS:
+        n, kind = WORKLOADS[name]
+        try:
+            inp = make_input(codec, name)
+            arm = OneGpu(codec, n, stream)
+            enc_ms, dec_ms, got, c = [], [], 0, 0
+            for i in range(2 + steps):
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                c = arm.encode(inp)
+                e1.record()
+                got, _ = arm.decode()
+                e2.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    enc_ms.append(e0.elapsed_time(e1))
+                    dec_ms.append(e1.elapsed_time(e2))
+            te, td = statistics.mean(enc_ms), statistics.mean(dec_ms)
+            row = {"workload": name, "bytes": n, "compressed_bytes": int(c), "encode_ms": te, "decode_ms": td,
+                   "encode_gbs": n / 1e6 / te, "decode_gbs": n / 1e6 / td, "round_trip_gbs": n / 1e6 / (te + td),
+                   "encode_frac": (2 * n + c) / 1e6 / te / peak, "decode_frac": (c + got) / 1e6 / td / peak,
+                   "rounds": codec.last_decode_rounds, "verified_round_trip": verify_one(codec, arm, inp, n, got, kind)}
+            if n < (126 << 20):
+                row["note"] = "fits the 126 MB L2: launch-latency bound, the HBM fraction is not meaningful"
+            if kind == "uniform256":
+                row["note"] = "all 256 byte values: the reference drops one symbol (encode.zig:70); round trip == text without it"
+            out.append(row)
+            del arm, inp
+            torch.cuda.empty_cache()
+        except Exception as exc:  # a config that cannot run must not take the headline down with it
+            out.append({"workload": name, "error": f"{type(exc).__name__}: {exc}"})
+    return out
+
+
 def run_ours(args, rank, world):
     import torch
 
@@ -328,17 +410,7 @@ def run_ours(args, rank, world):
     n = plan.n_local
     stream = torch.cuda.current_stream().cuda_stream
     thr = thresholds(kind) if kind != "file" else None
-
-    # ---- synthetic input, generated on the device (same bytes as entreepy_b200/synth.py on the CPU)
-    inp = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
-    if kind == "file":
-        data = host_sample(kind, n_total)[plan.lo:plan.hi]
-        inp[:n].copy_(torch.from_numpy(data.copy()))
-    elif kind == "fib32" and world == 1:
-        # exact counts, shuffled: the Huffman tree is a chain of depth 32 — i.i.d. sampling is not
-        inp[:n].copy_(synth.shuffled_dev(synth.fibonacci_counts(n, 32)))
-    else:
-        codec.synth_dev(inp.data_ptr(), n, synth.SEED, plan.lo, thr)
+    inp = make_input(codec, args.workload, plan.lo, n, world)
     arm = OneGpu(codec, n, stream) if world == 1 else ManyGpus(codec, plan, dist, stream)
 
     def barrier():
@@ -351,6 +423,8 @@ def run_ours(args, rank, world):
         e0.record()
         c_local = arm.encode(inp)
         ms_enc = codec.last_stage_ms()
+        if world > 1:  # the shard call times only its pack; the histogram is a call of its own
+            ms_enc[0] = getattr(arm.coder.backend, "hist_ms", 0.0)
         e1.record()
         got, offset = arm.decode()
         ms_dec = codec.last_stage_ms() + [codec.last_decode_rounds]
@@ -366,15 +440,7 @@ def run_ours(args, rank, world):
     barrier()
     # round trip == original (north_star): the text this rank decoded is text[offset : offset + got]
     if world == 1:
-        verified = got == n and bool(torch.equal(arm.dec[:n], inp[:n]))
-        if not verified and kind == "uniform256":
-            # all 256 byte values occur: the reference encoder gives the last symbol in sort order no code
-            # (encode.zig:70), so the round trip is the text WITHOUT that symbol — by construction
-            counts = codec.histogram_dev(inp.data_ptr(), n)
-            cb = et.build_codebook(counts)
-            dropped = [s for s in range(256) if counts[s] and cb.code[s].length == 0]
-            keep = inp[:n][inp[:n] != dropped[0]] if len(dropped) == 1 else inp[:0]
-            verified = len(dropped) == 1 and got == keep.numel() and bool(torch.equal(arm.dec[:got], keep))
+        verified = verify_one(codec, arm, inp, n, got, kind)
     else:
         want = torch.empty(got + 16, dtype=torch.uint8, device="cuda")
         if kind == "file":
@@ -388,9 +454,22 @@ def run_ours(args, rank, world):
     if not verified:
         raise SystemExit("bench.py: decode(encode(x)) != x — refusing to report a throughput")
 
-    launches0 = codec.kernel_launches
     stats = []
     with ClockSampler(local) as clocks:
+        # nvidia-smi takes a few hundred ms to deliver its first row and the timed region may be shorter than that
+        # (8 GPUs: ~2 ms per step): keep the same load running, untimed, until samples arrive, so that the clocks
+        # line describes the GPU under this load
+        t_wait = time.perf_counter()
+        while True:
+            done = len(clocks.rows) >= 3 or time.perf_counter() - t_wait >= 3.0 or clocks.proc is None
+            if dist is not None:  # rank 0 decides: every rank takes the same number of steps
+                flag = torch.tensor([int(done)], device="cuda")
+                dist.broadcast(flag, 0)
+                done = bool(int(flag.item()))
+            if done:
+                break
+            step()
+        launches0 = codec.kernel_launches
         barrier()
         t_begin = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
@@ -422,7 +501,9 @@ def run_ours(args, rank, world):
         ach = alg_bytes / 1e9 / (ms / 1e3) if ms > 0 else 0.0
         traffic = traffic_for(kernels) if (world == 1 and args.workload == "text-1G") else None
         return {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "algorithmic_bytes": alg_bytes, "ms": ms, "peak_source": peak_src}
+                "traffic": traffic, "traffic_source": "profiles/traffic.json (committed ncu --set full capture, not measured in this run)"
+                if traffic is not None else None,
+                "algorithmic_bytes": alg_bytes, "ms": ms, "peak_source": peak_src}
 
     roofs = [roof("pack (run_bits_kernel + pack_runs_kernel)", ["run_bits_kernel", "pack_runs_kernel"], n + c_local, pack_ms),
              roof("unpack (region_sync_kernel + region_write_kernel)", ["region_sync_kernel", "region_write_kernel"],
@@ -436,6 +517,9 @@ def run_ours(args, rank, world):
     if not args.no_e2e:
         e2e = run_e2e(args, arm, inp, n, n_total, world, dist, barrier)
 
+    configs = None
+    if world == 1 and args.workload == "text-1G" and not args.no_configs:
+        configs = run_other_configs(codec, stream, peak)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         k = min(n, CPU_SAMPLE)
@@ -463,6 +547,11 @@ def run_ours(args, rank, world):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "verified_round_trip": verified,
             "decode_check_rounds": stats[-1][4][4], "clocks": clocks.summary(),
         }
+        if configs is not None:
+            line["configs"] = configs
+            base = [c for c in configs if c.get("workload") == "text-4G" and "round_trip_gbs" in c]
+            if base:  # the one-GPU figure of the workload the N>1 runs shard: the denominator of strong scaling
+                line["scale_base_gbs"] = base[0]["round_trip_gbs"]
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -519,6 +608,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (text-5M, adversarial, text-4G)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

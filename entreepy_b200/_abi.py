@@ -12,11 +12,12 @@ ERR_CORRUPT, ERR_TOO_LARGE, ERR_UNSUPPORTED, ERR_INVALID_ARG = 6, 7, 8, 9
 
 FLAG_WRITE_OUTPUT, FLAG_PRINT_OUTPUT, FLAG_DEBUG = 0x1, 0x2, 0x4
 FLAG_QUIET, FLAG_NO_SCRATCH_LIMIT, FLAG_VALIDATE, FLAG_TIMING = 0x100, 0x200, 0x400, 0x800
+TUNE_LANE_MIN_BYTES, TUNE_DEBUG = 1, 2
 
 # every symbol include/entreepy_b200.h declares
 SYMBOLS = [
     "et_abi_version", "et_strerror", "et_ctx_create", "et_ctx_destroy", "et_last_error", "et_ctx_set_output_fd",
-    "et_ctx_kernel_launches", "et_ctx_last_stage_ms", "et_ctx_last_decode_rounds", "et_alloc_pinned", "et_free_pinned", "et_build_codebook",
+    "et_ctx_kernel_launches", "et_ctx_last_stage_ms", "et_ctx_last_decode_rounds", "et_ctx_set_tuning", "et_alloc_pinned", "et_free_pinned", "et_build_codebook",
     "et_header_size", "et_write_header", "et_encode_bound", "et_parse_header", "et_histogram", "et_histogram_dev",
     "et_encode", "et_decode", "et_encode_dev", "et_decode_dev", "et_pack_shard_dev", "et_shard_bits",
     "et_unpack_shard_dev", "et_synth_dev",
@@ -48,6 +49,7 @@ class Dictionary(ctypes.Structure):
         ("code", ctypes.c_uint64 * 256),
         ("min_length", ctypes.c_uint32),
         ("max_length", ctypes.c_uint32),
+        ("truncated", ctypes.c_uint32),
     ]
 
 
@@ -77,6 +79,7 @@ def load():
         "et_ctx_kernel_launches": (u64, [vp]),
         "et_ctx_last_stage_ms": (i, [vp, ctypes.POINTER(ctypes.c_float * 4)]),
         "et_ctx_last_decode_rounds": (u32, [vp]),
+        "et_ctx_set_tuning": (i, [vp, i, ctypes.c_longlong]),
         "et_alloc_pinned": (i, [sz, ctypes.POINTER(vp)]),
         "et_free_pinned": (None, [vp]),
         "et_build_codebook": (i, [vp, ctypes.POINTER(Codebook)]),

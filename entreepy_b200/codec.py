@@ -48,10 +48,12 @@ class DecodeFlags:  # decode.zig:7-11
     print_output: bool = False
     debug: bool = False
     quiet: bool = True
+    validate: bool = False  # extension: the input validation main.zig:199 leaves as a TODO
 
     def bits(self):
         return ((_abi.FLAG_WRITE_OUTPUT if self.write_output else 0) | (_abi.FLAG_PRINT_OUTPUT if self.print_output else 0)
-                | (_abi.FLAG_DEBUG if self.debug else 0) | (_abi.FLAG_QUIET if self.quiet else 0))
+                | (_abi.FLAG_DEBUG if self.debug else 0) | (_abi.FLAG_QUIET if self.quiet else 0)
+                | (_abi.FLAG_VALIDATE if self.validate else 0))
 
 
 def _u8(data):
@@ -141,6 +143,11 @@ class Codec:
         ms = (ctypes.c_float * 4)()
         self._lib.et_ctx_last_stage_ms(self._ctx, ctypes.byref(ms))
         return list(ms)
+
+    def set_tuning(self, key, value):
+        """et_ctx_set_tuning: _abi.TUNE_LANE_MIN_BYTES (0 sends every stream through the lane-interleaved
+        decoder, -1 restores the default), _abi.TUNE_DEBUG."""
+        self._check(self._lib.et_ctx_set_tuning(self._ctx, key, int(value)))
 
     def set_output_fd(self, fd):
         self._check(self._lib.et_ctx_set_output_fd(self._ctx, fd))

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -22,7 +23,7 @@ struct et_ctx {
     cudaStream_t stream = nullptr;       // context-owned stream (used when the caller passes none)
     cudaStream_t copy_stream = nullptr;  // second stream for overlapped host copies (uploads)
     cudaStream_t copy_stream2 = nullptr; // third stream: downloads, so that both directions of the link run at once
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[8] = {};
     // device scratch, grown on demand
     void *d_scratch = nullptr;
     size_t scratch_cap = 0;
@@ -35,6 +36,8 @@ struct et_ctx {
     uint64_t launches = 0;
     float stage_ms[4] = {0, 0, 0, 0};
     uint32_t last_decode_rounds = 0;  // passes over the chunk entries in the last decode (2 = guesses + one repair round sufficed)
+    UnpackTuning tune;                // device properties + et_ctx_set_tuning() knobs
+    uint32_t fixed_len = 0;           // the uploaded decoder tables are a complete code whose codes all have this length (0: not so)
     char err[512] = {0};
 };
 
@@ -256,6 +259,9 @@ extern "C" int et_ctx_create(int device, et_ctx **out) {
     for (auto &e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     ok = ok && cudaMalloc(reinterpret_cast<void **>(&ctx->d_small), kSmallBytes) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_small), kSmallBytes, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && unpack_init_device(device, &ctx->tune) == cudaSuccess;
+    if (const char *v = getenv("ET_LANE_MIN_BYTES")) ctx->tune.lane_min_bytes = atoll(v);  // read once, here
+    if (getenv("ET_DEBUG_LANES")) ctx->tune.debug = 1;
     if (!ok) {
         et_ctx_destroy(ctx);
         return ET_ERR_CUDA;
@@ -296,6 +302,15 @@ extern "C" int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]) {
 
 extern "C" uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx) { return ctx ? ctx->last_decode_rounds : 0; }
 
+extern "C" int et_ctx_set_tuning(et_ctx *ctx, int key, long long value) {
+    if (!ctx) return ET_ERR_INVALID_ARG;
+    switch (key) {
+        case ET_TUNE_LANE_MIN_BYTES: ctx->tune.lane_min_bytes = value; return ET_OK;
+        case ET_TUNE_DEBUG: ctx->tune.debug = value != 0; return ET_OK;
+    }
+    return fail(ctx, ET_ERR_INVALID_ARG, "unknown tuning key %d", key);
+}
+
 extern "C" int et_alloc_pinned(size_t bytes, void **out) {
     if (!out) return ET_ERR_INVALID_ARG;
     *out = nullptr;
@@ -315,7 +330,12 @@ extern "C" int et_histogram_dev(et_ctx *ctx, const void *d_in, size_t n, uint64_
     if (!ctx || !counts || (!d_in && n)) return ET_ERR_INVALID_ARG;
     ET_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    return histogram_dev(ctx, d_in, n, counts, s);
+    cudaEventRecord(ctx->ev[6], s);
+    const int rc = histogram_dev(ctx, d_in, n, counts, s);  // blocks until the counts are on the host
+    cudaEventRecord(ctx->ev[7], s);
+    ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = ctx->stage_ms[3] = 0.f;
+    if (rc == ET_OK && cudaEventSynchronize(ctx->ev[7]) == cudaSuccess) cudaEventElapsedTime(&ctx->stage_ms[0], ctx->ev[6], ctx->ev[7]);
+    return rc;
 }
 
 extern "C" int et_histogram(et_ctx *ctx, const uint8_t *in, size_t n, uint64_t counts[256]) {
@@ -456,14 +476,19 @@ extern "C" int et_pack_shard_dev(et_ctx *ctx, const void *d_in, size_t n, const 
 // ====================================================================== decode
 namespace {
 
-// Build the decoder tables for `dict` and queue their upload on `s`.
-int upload_unpack_tables(et_ctx *ctx, const et_dictionary &dict, cudaStream_t s) {
+// Build the decoder tables for `dict` and queue their upload on `s`.  validate: ET_FLAG_VALIDATE was passed.
+int upload_unpack_tables(et_ctx *ctx, const et_dictionary &dict, cudaStream_t s, bool validate = false) {
     UnpackTables *t = new (std::nothrow) UnpackTables;
     if (!t) return ET_ERR_OUT_OF_MEMORY;
     int rc = make_unpack_tables(dict, t);
+    if (rc == ET_OK && validate && !t->prefix_free) rc = ET_ERR_CORRUPT;
+    if (rc == ET_OK && validate && !t->complete) rc = ET_ERR_CORRUPT;
     if (rc != ET_OK) {
+        const bool why_incomplete = rc == ET_ERR_CORRUPT && validate && t->prefix_free;
         delete t;
-        return fail(ctx, rc, rc == ET_ERR_UNSUPPORTED ? "dictionary code longer than 32 bits" : "dictionary is not a prefix code");
+        return fail(ctx, rc, rc == ET_ERR_UNSUPPORTED ? "dictionary code longer than 32 bits"
+                             : why_incomplete        ? "dictionary is not a complete code (Kraft sum != 1)"
+                                                     : "dictionary is not a prefix code");
     }
     std::memcpy(ctx->h_small + kOffLut, t->clut, sizeof t->clut);
     std::memcpy(ctx->h_small + kOffLut + sizeof t->clut, t->wlut, sizeof t->wlut);
@@ -471,6 +496,7 @@ int upload_unpack_tables(et_ctx *ctx, const et_dictionary &dict, cudaStream_t s)
     std::memcpy(ctx->h_small + kOffSlots, t->slot_of, sizeof t->slot_of);
     std::memcpy(ctx->h_small + kOffSlots + sizeof t->slot_of, t->sub, sizeof t->sub);
     const size_t tbl_bytes = sizeof t->clut + sizeof t->wlut + (size_t)t->n_nodes * 4;
+    ctx->fixed_len = (t->complete && t->prefix_free && dict.min_length == dict.max_length) ? dict.max_length : 0u;
     delete t;
     ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffLut, ctx->h_small + kOffLut, tbl_bytes, cudaMemcpyHostToDevice, s));
     ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffSlots, ctx->h_small + kOffSlots, kOffThresholds - kOffSlots, cudaMemcpyHostToDevice, s));
@@ -482,12 +508,12 @@ int upload_unpack_tables(et_ctx *ctx, const et_dictionary &dict, cudaStream_t s)
 // pipelined host path does it before it queues the bulk uploads, which would otherwise delay it).
 int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, uint8_t *d_out, uint64_t max_symbols,
                uint64_t *n_symbols, cudaStream_t s, StageTimer *tm = nullptr, uint32_t *entry_exit = nullptr,
-               bool tables_ready = false) {
-    int rc = tables_ready ? ET_OK : upload_unpack_tables(ctx, dict, s);
+               bool tables_ready = false, bool validate = false, uint64_t *found = nullptr) {
+    int rc = tables_ready ? ET_OK : upload_unpack_tables(ctx, dict, s, validate);
     if (rc != ET_OK) return rc;
     if (tm) tm->mark(2);
 
-    const uint32_t chunk_bytes = unpack_chunk_bytes(g, ctx->num_sms, dict.min_length, dict.max_length);
+    const uint32_t chunk_bytes = unpack_chunk_bytes(g, ctx->tune, dict.min_length, dict.max_length);
     rc = ensure_scratch(ctx, unpack_scratch_bytes(g, chunk_bytes));
     if (rc != ET_OK) return rc;
     const uint32_t *d_clut = reinterpret_cast<const uint32_t *>(ctx->d_small + kOffLut);
@@ -497,7 +523,7 @@ int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, 
     uint32_t rounds = 0;
     const uint16_t *d_slots = reinterpret_cast<const uint16_t *>(ctx->d_small + kOffSlots);
     ET_CUDA(ctx, launch_unpack(g, chunk_bytes, d_clut, d_wlut, d_nodes, d_slots, d_out, max_symbols, ctx->d_scratch,
-                               ctx->h_small + kOffFlags, s, &launches, &rounds));
+                               ctx->h_small + kOffFlags, s, ctx->tune, ctx->fixed_len, &launches, &rounds));
     ctx->launches += (uint64_t)launches;
     ctx->last_decode_rounds = rounds;
     // launch_unpack left the stream idle and a copy of the scratch header in the pinned block:
@@ -509,6 +535,25 @@ int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, 
     if (entry_exit) std::memcpy(entry_exit, ctx->h_small + kOffFlags + 24, 8);
     if (flags & kErrInvalidCode) return fail(ctx, ET_ERR_CORRUPT, "body contains a bit pattern that is not a code");
     *n_symbols = std::min<uint64_t>(total, max_symbols);
+    if (found) *found = total;
+    return ET_OK;
+}
+
+// What is known about a stream before its body is touched.  Returns ET_OK with *empty = true when there is
+// nothing to decode: the dictionary ended early (decode.zig:66 just runs out of bytes; the reference's own
+// output for a single distinct symbol reads back like this) — the reference then returns 0 bytes.
+int check_stream(et_ctx *ctx, const et_dictionary &dict, size_t n, uint32_t flags, bool *empty) {
+    *empty = dict.truncated || dict.n_entries == 0;
+    if (dict.body_offset > n) return fail(ctx, ET_ERR_CORRUPT, "dictionary runs past the end of the stream");
+    if (!(flags & ET_FLAG_VALIDATE)) return ET_OK;
+    if (*empty) {
+        if (dict.n_entries == 0 && n == 5) return ET_OK;  // the 9-byte file of a single distinct symbol (encode.zig:270-275)
+        return fail(ctx, ET_ERR_CORRUPT, "the stream ends inside its dictionary (%u entries read)", dict.n_entries);
+    }
+    const uint64_t body_bits = (uint64_t)(n - dict.body_offset) * 8;
+    if ((uint64_t)dict.body_len * dict.min_length > body_bits)
+        return fail(ctx, ET_ERR_CORRUPT, "body of %zu bytes cannot hold %u symbols of at least %u bits", n - (size_t)dict.body_offset,
+                    dict.body_len, dict.min_length);
     return ET_OK;
 }
 
@@ -531,14 +576,15 @@ extern "C" int et_decode_dev(et_ctx *ctx, const void *d_in, size_t n, void *d_ou
     et_dictionary dict;
     int rc = et_parse_header(h_header, head, &dict);
     if (rc != ET_OK) return fail(ctx, rc, "cannot parse the .et dictionary");
-    if (dict.body_offset > n) return fail(ctx, ET_ERR_CORRUPT, "dictionary runs past the end of the stream");
+    bool empty = false;
+    if ((rc = check_stream(ctx, dict, n, flags, &empty)) != ET_OK) return rc;
     tm.mark(1);
-    if (!(flags & ET_FLAG_WRITE_OUTPUT)) return ET_OK;  // dry run: bytes_written stays 0 (decode.zig:185-188)
+    if (!(flags & ET_FLAG_WRITE_OUTPUT) || empty) return ET_OK;  // dry run: bytes_written stays 0 (decode.zig:185-188)
     if (!d_out && cap) return ET_ERR_INVALID_ARG;
     uint64_t produced = 0;
     const uint64_t want = std::min<uint64_t>(dict.body_len, cap);
     rc = unpack_dev(ctx, unpack_geometry(static_cast<const uint8_t *>(d_in) + dict.body_offset, n - dict.body_offset), dict,
-                    static_cast<uint8_t *>(d_out), want, &produced, s, &tm);  // D3
+                    static_cast<uint8_t *>(d_out), want, &produced, s, &tm, nullptr, false, (flags & ET_FLAG_VALIDATE) != 0);  // D3
     if (rc != ET_OK) return rc;
     tm.mark(3);
     ET_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
@@ -562,10 +608,12 @@ extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
     et_dictionary dict;
     int rc = et_parse_header(in, n, &dict);  // D1+D2 straight from the caller's buffer
     if (rc != ET_OK) return fail(ctx, rc, "cannot parse the .et dictionary");
-    if (dict.body_offset > n) return fail(ctx, ET_ERR_CORRUPT, "dictionary runs past the end of the stream");
+    bool empty = false;
+    if ((rc = check_stream(ctx, dict, n, flags, &empty)) != ET_OK) return rc;
     const bool write_out = (flags & ET_FLAG_WRITE_OUTPUT) != 0, print_out = (flags & ET_FLAG_PRINT_OUTPUT) != 0;
+    const bool validate = (flags & ET_FLAG_VALIDATE) != 0;
     uint64_t produced = 0;
-    if (write_out || print_out) {
+    if ((write_out || print_out) && !empty) {
         const size_t body_bytes = n - dict.body_offset;
         const uint64_t want = write_out ? std::min<uint64_t>(dict.body_len, cap) : dict.body_len;
         rc = ensure_bulk(ctx, &ctx->d_in, &ctx->d_in_cap, body_bytes + 16);
@@ -582,7 +630,7 @@ extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
         if (n_slices == 1) {
             if (body_bytes)
                 ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, in + dict.body_offset, body_bytes, cudaMemcpyHostToDevice, s));
-            rc = unpack_dev(ctx, unpack_geometry(ctx->d_in, body_bytes), dict, ctx->d_out, want, &produced, s);
+            rc = unpack_dev(ctx, unpack_geometry(ctx->d_in, body_bytes), dict, ctx->d_out, want, &produced, s, nullptr, nullptr, false, validate);
             if (rc != ET_OK) return rc;
             if (write_out) {
                 if (produced == cap && dict.body_len > cap)
@@ -591,7 +639,7 @@ extern "C" int et_decode(et_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
                 ET_CUDA(ctx, cudaStreamSynchronize(s));
             }
         } else {
-            rc = upload_unpack_tables(ctx, dict, s);  // before the bulk uploads: copies in one direction run in issue order
+            rc = upload_unpack_tables(ctx, dict, s, validate);  // before the bulk uploads: copies in one direction run in issue order
             if (rc != ET_OK) return rc;
             std::vector<cudaEvent_t> up(n_slices, nullptr);
             auto cleanup = [&]() {
@@ -666,20 +714,27 @@ extern "C" int et_unpack_shard_dev(et_ctx *ctx, const void *d_range, size_t rang
         return fail(ctx, ET_ERR_INVALID_ARG, "shard geometry: 16-byte aligned range, 32-byte aligned owned part, 32 bytes of look-ahead");
     if (head_bit >= 0 && ((uint64_t)head_bit < own_begin_byte * 8 || (uint64_t)head_bit >= own_begin_byte * 8 + 64))
         return fail(ctx, ET_ERR_INVALID_ARG, "head_bit must lie in the first 64 bits of the owned part");
+    if (dict->n_entries == 0 || dict->truncated) {  // nothing can be decoded (decode.zig:66 ran out of dictionary bytes)
+        *n_symbols = 0;
+        if (entry_bit) *entry_bit = (uint64_t)own_begin_byte * 8;
+        if (exit_bit) *exit_bit = (uint64_t)own_end_byte * 8;
+        return ET_OK;
+    }
     ET_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     StageTimer tm{ctx, s, true};
     tm.mark(0);
     tm.mark(1);
     const UnpackGeometry g = unpack_geometry_shard(d_range, range_bytes, own_begin_byte, own_end_byte, (long long)head_bit);
-    uint64_t produced = 0;
+    uint64_t produced = 0, found = 0;
     uint32_t ee[2] = {0, 0};
-    const int rc = unpack_dev(ctx, g, *dict, static_cast<uint8_t *>(d_out), cap, &produced, s, &tm, ee);
+    const int rc = unpack_dev(ctx, g, *dict, static_cast<uint8_t *>(d_out), cap, &produced, s, &tm, ee, false, false, &found);
     if (rc != ET_OK) return rc;
     tm.mark(3);
     ET_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
     tm.finish(4);
-    *n_symbols = produced;
+    *n_symbols = found;  // the caller's text offsets are sums of these: never a clipped count
+    if (found > cap) return fail(ctx, ET_ERR_NO_SPACE, "NoSpaceLeft: the shard holds %llu symbols, capacity %zu", (unsigned long long)found, cap);
     // entry: bits past the first bit of the 32-byte sector grid the chunks are cut on (= own_begin: it is 32-byte aligned)
     if (entry_bit) *entry_bit = (uint64_t)own_begin_byte * 8 + ee[0];
     if (exit_bit) *exit_bit = (uint64_t)own_end_byte * 8 + ee[1];

@@ -27,11 +27,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
 // 16 aligned bytes of which only [lo, hi) (byte offsets relative to p) may be touched; the

@@ -176,12 +176,24 @@ extern "C" int et_parse_header(const uint8_t *in, size_t n, et_dictionary *dict)
     dict->body_len = ((uint32_t)in[1] << 24) | ((uint32_t)in[2] << 16) | ((uint32_t)in[3] << 8) | in[4];
     BitSource src{in, n * 8, 40};
     uint32_t lo = 0xFFFFFFFFu, hi = 0;
-    for (uint32_t e = 0; e < dict->n_entries; ++e) {  // decode.zig:66-141
-        uint64_t sym, len, code;
-        if (!src.take(8, &sym) || !src.take(8, &len)) return ET_ERR_CORRUPT;
-        if (len == 0) return ET_ERR_CORRUPT;
-        if (len > 64) return ET_ERR_UNSUPPORTED;
-        if (!src.take((unsigned)len, &code)) return ET_ERR_CORRUPT;
+    const uint32_t announced = dict->n_entries;
+    for (uint32_t e = 0; e < announced; ++e) {  // decode.zig:66-141
+        uint64_t sym = 0, len = 0, code = 0;
+        // The reference's state machine simply stops when the bytes run out (decode.zig:66,135-140): the entries
+        // read so far stand and the body is empty, so nothing is decoded and no error is raised.  This is also how
+        // its own output for a single distinct symbol reads back (9-byte file, zero entries, encode.zig:270-275).
+        bool whole = src.take(8, &sym) && src.take(8, &len);
+        if (whole && len > 64) return ET_ERR_UNSUPPORTED;
+        whole = whole && src.take((unsigned)len, &code);
+        if (!whole) {
+            dict->n_entries = e;
+            dict->truncated = 1;
+            dict->min_length = e ? lo : 0;
+            dict->max_length = hi;
+            dict->body_offset = n;
+            return ET_OK;
+        }
+        if (len == 0) return ET_ERR_CORRUPT;  // the reference indexes entry[len - 1] (decode.zig:124): out of bounds
         dict->symbol[e] = (uint8_t)sym;
         dict->length[e] = (uint8_t)len;
         dict->code[e] = code;
@@ -229,32 +241,55 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
     t->max_length = dict.max_length;
     t->min_length = dict.min_length;
 
-    // Binary trie over the dictionary codes; rejects anything that is not a prefix code.
+    // Binary trie over the dictionary codes.  The reference decoder accepts any dictionary: it tries code
+    // lengths from the shortest up (decode.zig:175-181), so where one entry is a prefix of another the shorter
+    // one always matches first and the longer one can never be reached, and a repeated (length, code) pair
+    // overwrites the earlier symbol (decode.zig:123-125).  The same rules here; `prefix_free` records whether
+    // they were needed (ET_FLAG_VALIDATE turns that into an error).
     static_assert(kMaxTrieNodes >= 1 + 255 * 32, "trie capacity");
     uint16_t kid[kMaxTrieNodes][2];
     uint32_t n_nodes = 1;
     kid[0][0] = kid[0][1] = kChildNone;
     uint64_t kraft = 0;  // in units of 2^-32
+    t->prefix_free = true;
+    bool reachable[256];
     for (uint32_t e = 0; e < dict.n_entries; ++e) {
         const unsigned len = dict.length[e];
         if (len == 0) return ET_ERR_CORRUPT;
         kraft += 1ull << (32 - len);
+        reachable[e] = true;
         uint32_t node = 0;
         for (unsigned k = len; k > 0; --k) {
             const unsigned b = (unsigned)((dict.code[e] >> (k - 1)) & 1u);
             uint16_t &slot = kid[node][b];
             if (k == 1) {
-                if (slot != kChildNone) return ET_ERR_CORRUPT;  // duplicate code or prefix of another
+                if (slot != kChildNone) t->prefix_free = false;  // repeated code, or a prefix of longer ones: this entry wins
                 slot = (uint16_t)(kChildLeaf | dict.symbol[e]);
             } else {
                 if (slot == kChildNone) {
                     kid[n_nodes][0] = kid[n_nodes][1] = kChildNone;
                     slot = (uint16_t)n_nodes++;
                 } else if (slot & kChildLeaf) {
-                    return ET_ERR_CORRUPT;  // a shorter code is a prefix of this one
+                    t->prefix_free = false;  // a shorter code is a prefix of this one: never reached
+                    reachable[e] = false;
+                    break;
                 }
                 node = slot;
             }
+        }
+    }
+    // an entry that lost its place to a later, shorter one (the leaf replaced the subtree it sat in)
+    for (uint32_t e = 0; e < dict.n_entries; ++e) {
+        if (!reachable[e]) continue;
+        uint32_t node = 0;
+        for (unsigned k = dict.length[e]; k > 0 && reachable[e]; --k) {
+            const uint16_t slot = kid[node][(dict.code[e] >> (k - 1)) & 1u];
+            if (k == 1)
+                reachable[e] = slot == (uint16_t)(kChildLeaf | dict.symbol[e]);
+            else if (slot == kChildNone || (slot & kChildLeaf))
+                reachable[e] = false;
+            else
+                node = slot;
         }
     }
     t->n_nodes = n_nodes;
@@ -268,7 +303,7 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
     std::memset(first, 0, sizeof first);
     for (uint32_t e = 0; e < dict.n_entries; ++e) {
         const unsigned len = dict.length[e];
-        if (len > (unsigned)kLutBits) continue;
+        if (len > (unsigned)kLutBits || !reachable[e]) continue;
         const uint32_t lo = (uint32_t)(dict.code[e] << (kLutBits - len)), n = 1u << (kLutBits - len);
         for (uint32_t w = lo; w < lo + n; ++w) first[w] = (uint16_t)((len << 8) | dict.symbol[e]);
     }
@@ -277,7 +312,7 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
     for (uint32_t w = 0; w < (uint32_t)kLutSize; ++w) stuck[w] = (uint16_t)kChildNone;
     for (uint32_t e = 0; e < dict.n_entries; ++e) {
         const unsigned len = dict.length[e];
-        if (len <= (unsigned)kLutBits) continue;
+        if (len <= (unsigned)kLutBits || !reachable[e]) continue;
         const uint32_t w = (uint32_t)(dict.code[e] >> (len - kLutBits));
         if (stuck[w] != kChildNone) continue;
         uint32_t node = 0;
@@ -316,7 +351,7 @@ int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
     // table of its first kLutBits bits
     for (uint32_t e = 0; e < dict.n_entries; ++e) {
         const unsigned len = dict.length[e];
-        if (len <= (unsigned)kLutBits || len > (unsigned)kLutBits + kSubBits) continue;
+        if (len <= (unsigned)kLutBits || len > (unsigned)kLutBits + kSubBits || !reachable[e]) continue;
         const uint16_t slot = t->slot_of[(uint32_t)(dict.code[e] >> (len - kLutBits))];
         if (slot == kNoSlot) continue;
         const unsigned rest = len - kLutBits;  // bits of the code after the window

@@ -61,7 +61,8 @@ struct UnpackTables {
     uint32_t n_nodes;
     uint32_t max_length;
     uint32_t min_length;
-    bool complete;  // every window decodes (Kraft sum == 1)
+    bool complete;     // every window decodes (Kraft sum == 1)
+    bool prefix_free;  // no entry is a prefix (or a repeat) of another
 };
 
 int make_unpack_tables(const et_dictionary &dict, UnpackTables *t);

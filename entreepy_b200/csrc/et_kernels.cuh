@@ -69,8 +69,18 @@ UnpackGeometry unpack_geometry_shard(const void *d_range, size_t range_bytes, si
 
 constexpr uint32_t kErrInvalidCode = 2u;
 
+// Per-context decoder settings: device properties read once by unpack_init_device() and the knobs of
+// et_ctx_set_tuning().
+struct UnpackTuning {
+    long long lane_min_bytes = -1;  // bodies of at least this many bytes take the lane-interleaved decoder (-1: default)
+    int debug = 0;
+    int max_smem = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    int num_sms = 0;
+};
+cudaError_t unpack_init_device(int device, UnpackTuning *tune);
+
 // Chunk size for this stream (bytes per thread) and the device scratch the decoder needs.
-uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms, uint32_t min_length, uint32_t max_length);
+uint32_t unpack_chunk_bytes(const UnpackGeometry &g, const UnpackTuning &tune, uint32_t min_length, uint32_t max_length);
 size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes);
 // Scratch header after the call: [4] error flags (u32), [8] symbols found (u64), [24] entry used
 // by the first chunk, [28] exit of the last chunk (u32 bits).  Writes min(total, max_symbols)
@@ -78,9 +88,12 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes);
 // h_hdr (pinned host memory, 64 bytes) holds a copy of the first 32 bytes of the scratch header.
 // d_slots: UnpackTables::slot_of followed by UnpackTables::sub (second-level tables of the lane-interleaved decoder).
 // *rounds_out = passes over the chunk entries it took (2 = the guesses plus one repair round sufficed).
+// fixed_len: the dictionary is a complete code whose codes all have this many bits (0: it is not) — such a
+// stream never re-synchronises, but every chunk's entry follows from the first one in closed form.
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
                           const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
-                          uint8_t *h_hdr, cudaStream_t stream, int *launches, uint32_t *rounds_out);
+                          uint8_t *h_hdr, cudaStream_t stream, const UnpackTuning &tune, uint32_t fixed_len, int *launches,
+                          uint32_t *rounds_out);
 
 // ---------------------------------------------------------------- synthetic input generator
 cudaError_t launch_synth(uint8_t *d_out, size_t n, uint64_t seed, uint64_t first_index, const uint32_t *d_thresholds,

@@ -114,10 +114,6 @@ constexpr int kTableLanes = 16;
 constexpr int kTableBytes = 256 * kTableLanes * 8;                    // 32 KiB
 constexpr int kStageGuard = 4;                                        // zero words in front of the image
 
-struct PackShared {
-    uint32_t warp_sum[kWarps];
-};
-
 // 16 input bytes of thread `tid` of `tile`, and which of them exist (edge tiles only).
 __device__ __forceinline__ uint4 load_symbols(const PackArgs &a, uint32_t tile, uint32_t tid, bool interior,
                                               uint32_t *valid) {
@@ -473,15 +469,10 @@ __global__ void __launch_bounds__(kPackThreads) pack_wide_kernel(const PackArgs 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int i = tid; i < StageWords<WIDE>::value; i += kPackThreads) stage[i] = 0;
-    if constexpr (!WIDE) {
-        const uint32_t *src = static_cast<const uint32_t *>(a.tables);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(table);
-        for (int i = tid; i < 256 * 32; i += kPackThreads) dst[i] = src[i >> 5];
-    } else {
+    {
         const uint8_t *src = static_cast<const uint8_t *>(a.tables);
         for (int i = tid; i < PackCfg<true>::kTableBytes; i += kPackThreads) table[i] = src[i];
     }
-    const uint8_t *table_lane = table + lane * 4;
     const unsigned long long *wide_code = reinterpret_cast<const unsigned long long *>(table);
     const uint8_t *wide_len = table + 256 * 8;
 
@@ -504,7 +495,6 @@ __global__ void __launch_bounds__(kPackThreads) pack_wide_kernel(const PackArgs 
                                         : ld_partial_v4(a.in_aligned + v0, (int)max(lo, 0ll), (int)min(hi, 16ll));
         }
         const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
-        uint32_t ent[WIDE ? 1 : kPackItems];
         uint32_t my_bits = 0;
 #pragma unroll
         for (int i = 0; i < kPackItems; ++i) {
@@ -512,17 +502,8 @@ __global__ void __launch_bounds__(kPackThreads) pack_wide_kernel(const PackArgs 
             const int sh = 8 * (i & 3);
             bool valid = true;
             if (edge) valid = (v0 + i >= a.misalign) && (v0 + i < a.v_end);
-            if constexpr (!WIDE) {
-                // byte -> byte offset sym*128 into this lane's column of the table
-                const uint32_t off = sh == 0 ? ((w << 7) & 0x7f80u) : ((w >> (sh - 7)) & 0x7f80u);
-                uint32_t e = *reinterpret_cast<const uint32_t *>(table_lane + off);
-                if (!valid) e = 0;
-                ent[i] = e;
-                my_bits += e & 63u;
-            } else {
-                const uint32_t sym = (w >> sh) & 0xffu;
-                my_bits += valid ? wide_len[sym] : 0u;
-            }
+            const uint32_t sym = (w >> sh) & 0xffu;
+            my_bits += valid ? wide_len[sym] : 0u;
         }
 
         // ---- (2) block scan of bit totals, look-back for the tile's bit offset
@@ -567,15 +548,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_wide_kernel(const PackArgs 
             unsigned long long acc = 0;
 #pragma unroll
             for (int i = 0; i < kPackItems; ++i) {
-                if constexpr (!WIDE) {
-                    const uint32_t len = ent[i] & 63u;
-                    acc = (acc << len) | (ent[i] >> 6);
-                    fill += len;
-                    if (fill >= 32u) {
-                        fill -= 32u;
-                        atomicOr(wp++, (uint32_t)(acc >> fill));
-                    }
-                } else {
+                {
                     const uint32_t w = rw[i >> 2];
                     const uint32_t sym = (w >> (8 * (i & 3))) & 0xffu;
                     bool valid = true;

@@ -51,6 +51,7 @@ struct DecArgs {
     uint32_t head_known;
     uint32_t n_chunks;
     uint32_t chunk_bytes;         // multiple of 16
+    uint32_t fixed_len;           // > 0: every code has this length (complete code): entries in closed form, no run-up
     const uint32_t *clut;
     const uint32_t *wlut;
     const uint32_t *nodes;
@@ -453,7 +454,15 @@ __global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecA
     if (round != 0) *a.changed = 1u;
     const Chunk k = chunk_of(a, c);
     if (c == 0 && a.head_known) start = a.head_off;
-    const bool known = round != 0 || (c == 0 && a.head_known);
+    bool known = round != 0 || (c == 0 && a.head_known);
+    if (a.fixed_len && round == 0) {
+        // Codes of one length never re-synchronise (a wrong phase stays wrong for ever), but they need not: every
+        // boundary is a whole number of codes past the first one.  Without a known head the first entry is a guess
+        // (bit 0 of the owned part); the others are consistent with it, and the caller repairs the guess.
+        const uint64_t base = a.grid_bit + (a.head_known ? a.head_off : 0u);
+        if (k.begin > base) start = (uint32_t)((a.fixed_len - (k.begin - base) % a.fixed_len) % a.fixed_len);
+        known = true;
+    }
     uint32_t cnt = 0, entry = start, exit_bits = 0;
     if (k.interior) {
         const uint32_t s = count_chunk_fast(a, k, start, !known, smem_addr(clut_sh), &entry);
@@ -1323,6 +1332,17 @@ uint64_t chunk_count(const UnpackGeometry &g, uint32_t chunk_bytes) {
 
 }  // namespace
 
+// Once per context (the shared-memory opt-in of the two big kernels is a property of the function on the
+// context's device): what the device offers, and the attributes the launches rely on.
+cudaError_t unpack_init_device(int device, UnpackTuning *tune) {
+    cudaError_t err;
+    if ((err = cudaDeviceGetAttribute(&tune->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return err;
+    if ((err = cudaDeviceGetAttribute(&tune->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(region_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tune->max_smem)) != cudaSuccess)
+        return err;
+    return cudaFuncSetAttribute(region_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmem);
+}
+
 UnpackGeometry unpack_geometry(const void *d_body, size_t body_bytes) {
     UnpackGeometry g;
     const uintptr_t p = reinterpret_cast<uintptr_t>(d_body);
@@ -1353,12 +1373,11 @@ UnpackGeometry unpack_geometry_shard(const void *d_range, size_t range_bytes, si
 }
 
 // Streams of at least this many bytes take the lane-interleaved decoder (enough regions to give every
-// SM a full set of warps).  ET_LANE_MIN_BYTES overrides it (tests run the path on small inputs).
-static uint64_t lane_path_min_bytes(int num_sms) {
-    const char *v = getenv("ET_LANE_MIN_BYTES");
-    const long long env = v ? atoll(v) : -1ll;
-    if (env >= 0) return (uint64_t)env > 2 * kRegionBytes ? (uint64_t)env : 2 * kRegionBytes;
-    return (uint64_t)num_sms * 8 * kRegionBytes;
+// SM a full set of warps).  ET_TUNE_LANE_MIN_BYTES overrides it (tests run the path on small inputs).
+static uint64_t lane_path_min_bytes(const UnpackTuning &tune) {
+    if (tune.lane_min_bytes >= 0)
+        return (uint64_t)tune.lane_min_bytes > 2 * kRegionBytes ? (uint64_t)tune.lane_min_bytes : 2 * kRegionBytes;
+    return (uint64_t)tune.num_sms * 8 * kRegionBytes;
 }
 
 // Chunk size.  256 B suits codes that re-synchronise within a few symbols.  When all code
@@ -1366,10 +1385,11 @@ static uint64_t lane_path_min_bytes(int num_sms) {
 // codes, ~2 KB on average), and every fixpoint round repairs only one chunk's worth of it, so
 // such codes get chunks longer than their synchronisation distance.  Short streams get
 // shorter chunks so that the GPU is not left mostly idle.
-uint32_t unpack_chunk_bytes(const UnpackGeometry &g, int num_sms, uint32_t min_length, uint32_t max_length) {
+uint32_t unpack_chunk_bytes(const UnpackGeometry &g, const UnpackTuning &tune, uint32_t min_length, uint32_t max_length) {
+    const int num_sms = tune.num_sms;
     const uint64_t bytes = (g.own_end_bit - g.own_begin_bit + 7) / 8;
     const uint32_t spread = max_length - min_length;
-    if (spread > 2 && bytes >= lane_path_min_bytes(num_sms)) return kLaneBytes;  // lane-interleaved decoder
+    if (spread > 2 && bytes >= lane_path_min_bytes(tune)) return kLaneBytes;  // lane-interleaved decoder
     uint32_t cb = spread <= 1 ? 4096u : spread == 2 ? 1024u : 256u;
     const uint32_t floor_cb = cb > 256u ? 256u : 32u;
     while (cb > floor_cb && bytes / cb < (uint64_t)num_sms * 2048) cb >>= 1;
@@ -1387,24 +1407,9 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
 // Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
 // look at the scratch header after the scan: the largest region sizes the text stage of a warp.
 static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, const void *d_header, uint8_t *h_hdr, cudaStream_t stream,
-                                       int *launches, uint32_t *rounds_out) {
-    // per device: the shared-memory opt-in of the two big kernels is a property of the function ON that device
-    static int smem_of[64] = {0}, sms_of[64] = {0};
+                                       const UnpackTuning &tune, int *launches, uint32_t *rounds_out) {
     cudaError_t err;
-    int dev = 0;
-    if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!smem_of[dev]) {
-        int smem = 0;
-        if ((err = cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
-        if ((err = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
-        if ((err = cudaFuncSetAttribute(region_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
-            return err;
-        if ((err = cudaFuncSetAttribute(region_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmem)) != cudaSuccess)
-            return err;
-        smem_of[dev] = smem;
-    }
-    const int max_smem = smem_of[dev], num_sms = sms_of[dev];
+    const int max_smem = tune.max_smem, num_sms = tune.num_sms;
     const uint32_t *h_changed = reinterpret_cast<const uint32_t *>(h_hdr + 16);
     const uint32_t sync_blocks = (n_regions + kSyncWarps - 1) / kSyncWarps;
     const uint32_t resident = (uint32_t)num_sms * 2u;  // __launch_bounds__(.., 2)
@@ -1436,7 +1441,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
         // one look at the scratch header: error flags, symbols found, "an entry was wrong", entry and exit of the shard
         if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
         if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
-        if (getenv("ET_DEBUG_LANES"))
+        if (tune.debug)
             fprintf(stderr, "[lanes] regions=%u chunks=%u max_sum=%u rounds=%u changed=%u\n", n_regions, a.n_chunks,
                     *reinterpret_cast<const uint32_t *>(h_hdr + 20), rounds, *h_changed);
         if (*h_changed == 0) break;  // every entry was the true one: what the write walk produced stands
@@ -1451,7 +1456,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
             if (launches) *launches += 1;
             if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
             if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
-            if (getenv("ET_DEBUG_LANES")) fprintf(stderr, "[lanes] repair rounds=%u changed=%u\n", rounds, *h_changed);
+            if (tune.debug) fprintf(stderr, "[lanes] repair rounds=%u changed=%u\n", rounds, *h_changed);
             if (*h_changed == 0) break;
             if (rounds > a.n_chunks + 8u) return cudaErrorUnknown;  // cannot happen: each round settles one more chunk
         }
@@ -1463,7 +1468,8 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
 
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
                           const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
-                          uint8_t *h_hdr, cudaStream_t stream, int *launches, uint32_t *rounds_out) {
+                          uint8_t *h_hdr, cudaStream_t stream, const UnpackTuning &tune, uint32_t fixed_len, int *launches,
+                          uint32_t *rounds_out) {
     uint32_t *h_flag = reinterpret_cast<uint32_t *>(h_hdr + 32);  // a word for the check rounds
     const uint64_t n64 = chunk_count(g, chunk_bytes);
     uint8_t *p = static_cast<uint8_t *>(scratch_base);
@@ -1488,6 +1494,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.head_off = (uint32_t)(g.head_bit - a.grid_bit);
     a.n_chunks = n;
     a.chunk_bytes = chunk_bytes;
+    a.fixed_len = fixed_len;
     a.clut = d_clut;
     a.wlut = d_wlut;
     a.nodes = d_nodes;
@@ -1509,7 +1516,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.out = d_out;
     a.max_symbols = max_symbols;
 
-    if (lanes) return launch_unpack_lanes(a, nb, p, h_hdr, stream, launches, rounds_out);
+    if (lanes) return launch_unpack_lanes(a, nb, p, h_hdr, stream, tune, launches, rounds_out);
 
     // Common case (codes that re-synchronise quickly): one walk from the guesses, one repair
     // round for the few chunks whose run-up was too short (text: 0.1 % of them; their exits do
@@ -1543,7 +1550,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     };
     // Long chunks were chosen because this code synchronises slowly: the guesses are known to be
     // poor, so settle the entries before spending a write walk on them.
-    if (chunk_bytes > 256u) {
+    if (chunk_bytes > 256u && !fixed_len) {
         err = settle();
         if (err != cudaSuccess) return err;
     }

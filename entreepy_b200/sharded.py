@@ -154,7 +154,9 @@ class GpuBackend:
         self.codec, self.stream = codec, stream
 
     def histogram(self, t_in, n):
-        return self.codec.histogram_dev(t_in.data_ptr(), n, self.stream)
+        counts = self.codec.histogram_dev(t_in.data_ptr(), n, self.stream)
+        self.hist_ms = self.codec.last_stage_ms()[0]  # et_histogram_dev times its own kernel + read-back
+        return counts
 
     def shard_bits(self, counts, cb):
         return self.codec.shard_bits(counts, cb)

@@ -53,7 +53,11 @@ typedef enum et_status {
 /* extensions (not in the reference) */
 #define ET_FLAG_QUIET 0x100u             /* suppress the "X => Y" stderr summary (encode.zig:334, decode.zig:217) */
 #define ET_FLAG_NO_SCRATCH_LIMIT 0x200u  /* lift the reference's 7200+n scratch bound (encode.zig:253) */
-#define ET_FLAG_VALIDATE 0x400u          /* decode: reject non-prefix / incomplete dictionaries up front */
+/* decode: the input validation the reference leaves as a TODO (main.zig:199).  With the flag a dictionary that is
+ * not a complete prefix code, or a body too short for body_len symbols, is ET_ERR_CORRUPT before anything is
+ * decoded.  Without it acceptance follows the reference: whatever parses is decoded (when two dictionary
+ * entries collide the shorter code wins, as decode.zig:181 tries lengths from the shortest up). */
+#define ET_FLAG_VALIDATE 0x400u
 #define ET_FLAG_TIMING 0x800u            /* *_dev calls: record per-stage CUDA events (et_ctx_last_stage_ms), print nothing */
 
 /* ------------------------------------------------------------------ code tables */
@@ -74,13 +78,14 @@ typedef struct et_codebook {
 
 /* Parsed .et dictionary (decode.zig:34-141).  `in` handed to the parser is file[4..]. */
 typedef struct et_dictionary {
-    uint32_t n_entries;    /* in[0] + 1 as u8 (decode.zig:34) */
+    uint32_t n_entries;    /* entries read: in[0] + 1 as u8 (decode.zig:34), fewer when the bytes ran out first */
     uint32_t body_len;     /* symbols to decode, BE u32 (decode.zig:36-42) */
     uint64_t body_offset;  /* byte offset of the body inside `in` (decode.zig:136,156) */
     uint8_t symbol[256];
     uint8_t length[256];
     uint64_t code[256];
     uint32_t min_length, max_length;
+    uint32_t truncated;    /* the stream ended inside the dictionary: the body is empty (decode.zig:66,135-140) */
 } et_dictionary;
 
 typedef struct et_ctx et_ctx;
@@ -99,13 +104,19 @@ ET_API uint64_t et_ctx_kernel_launches(const et_ctx *ctx);
 /* Milliseconds the last et_encode_dev / et_decode_dev call spent per stage, measured with
  * CUDA events on the launching stream.  encode: [0]=histogram kernel + 2 KiB read-back,
  * [1]=host codebook/header, [2]=pack + seam fix-up kernels.  decode: [0]=header read-back and
- * dictionary parse, [1]=table upload, [2]=decode kernels.  [3]=0.
- * Only filled when ET_FLAG_TIMING or ET_FLAG_DEBUG was passed. */
+ * dictionary parse, [1]=table upload, [2]=decode kernels.  [3]=0.  et_histogram_dev: [0]=kernel + read-back.
+ * et_encode_dev / et_decode_dev fill it only when ET_FLAG_TIMING or ET_FLAG_DEBUG was passed. */
 ET_API int et_ctx_last_stage_ms(const et_ctx *ctx, float ms[4]);
 
 /* Passes over the chunk entries in the last decode: 2 = the guessed entries plus one repair round were enough
  * (self-synchronising streams); more = that many fixpoint rounds were needed (slowly synchronising codes). */
 ET_API uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx);
+
+/* Tuning knobs of a context (tests and benchmarks; the defaults are what production wants).  The environment
+ * variables ET_LANE_MIN_BYTES and ET_DEBUG_LANES seed the first two when the context is created. */
+#define ET_TUNE_LANE_MIN_BYTES 1 /* bodies of at least this many bytes take the lane-interleaved decoder; -1 = default */
+#define ET_TUNE_DEBUG 2          /* non-zero: one line per decode on stderr */
+ET_API int et_ctx_set_tuning(et_ctx *ctx, int key, long long value);
 
 /* Pinned host memory for full-rate host<->device copies in et_encode/et_decode. */
 ET_API int et_alloc_pinned(size_t bytes, void **out);
@@ -167,7 +178,8 @@ ET_API uint64_t et_shard_bits(const uint64_t counts[256], const et_codebook *cb)
  * synchronises on the bytes before own_begin_byte (give it >= 32) and reports what it found.
  * *entry_bit = where the first owned codeword began, *exit_bit = first codeword boundary at or
  * after own_end_byte*8 (both from d_range): rank r's entry must equal rank r-1's exit, which the
- * host checks after one all-gather; a rank whose entry was wrong calls again with head_bit. */
+ * host checks after one all-gather; a rank whose entry was wrong calls again with head_bit.
+ * ET_ERR_NO_SPACE when the shard holds more than `cap` symbols (*n_symbols is then the number found). */
 ET_API int et_unpack_shard_dev(et_ctx *ctx, const void *d_range, size_t range_bytes, size_t own_begin_byte,
                         size_t own_end_byte, const et_dictionary *dict, int64_t head_bit, void *d_out, size_t cap,
                         uint64_t *n_symbols, uint64_t *entry_bit, uint64_t *exit_bit, void *stream);

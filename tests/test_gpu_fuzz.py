@@ -1,5 +1,5 @@
 """Seeded random inputs through the whole CUDA path (lane-run pack, lane-interleaved decoder forced on by
-ET_LANE_MIN_BYTES=0) against the oracle: random alphabets and skews, sizes around the region sizes (2048 symbols
+et_ctx_set_tuning(ET_TUNE_LANE_MIN_BYTES, 0)) against the oracle: random alphabets and skews, sizes around the region sizes (2048 symbols
 on encode, 4224 stream bytes on decode), every alignment of input, stream and output.  Bar: bit-exact."""
 import os
 
@@ -24,10 +24,16 @@ def _case(rng):
     return data
 
 
-def test_fuzz_encode_decode_against_oracle(codec, monkeypatch):
+@pytest.fixture()
+def lanes(codec):
+    codec.set_tuning(et._abi.TUNE_LANE_MIN_BYTES, 0)
+    yield
+    codec.set_tuning(et._abi.TUNE_LANE_MIN_BYTES, -1)
+
+
+def test_fuzz_encode_decode_against_oracle(codec, lanes):
     import torch
 
-    monkeypatch.setenv("ET_LANE_MIN_BYTES", "0")
     rng = np.random.default_rng(20261018)
     done = 0
     cases = int(os.environ.get("ET_FUZZ_CASES", "60"))

@@ -1,6 +1,6 @@
 """The lane-interleaved decoder (regions of 32 chunks per warp) on inputs of every shape.
 
-Long streams take it by default; ET_LANE_MIN_BYTES=0 sends short ones through it as well, so the
+Long streams take it by default; et_ctx_set_tuning(ET_TUNE_LANE_MIN_BYTES, 0) sends short ones through it as well, so the
 oracle can check it at sizes it finishes in seconds.  Bar: bit-exact (the original text).
 """
 import numpy as np
@@ -19,8 +19,10 @@ def _oracle_et(data):
 
 
 @pytest.fixture()
-def lanes(monkeypatch):
-    monkeypatch.setenv("ET_LANE_MIN_BYTES", "0")
+def lanes(codec):
+    codec.set_tuning(et._abi.TUNE_LANE_MIN_BYTES, 0)
+    yield
+    codec.set_tuning(et._abi.TUNE_LANE_MIN_BYTES, -1)
 
 
 def test_lane_decoder_on_the_oracle_cases(codec, lanes):

@@ -145,9 +145,86 @@ def test_decode_dry_run_writes_nothing(codec, golden_et):
 
 def test_decode_rejects_garbage(codec):
     with pytest.raises(et.EntreepyError):
-        codec.decode(b"\x01\x00\x00")
+        codec.decode(b"\x01\x00\x00")  # the reference indexes compressed_text[1..4] out of bounds (decode.zig:36-42)
+    # second entry truncated: the reference's dictionary state machine runs out of bytes (decode.zig:66), the body is
+    # empty and nothing is decoded - no error.  ET_FLAG_VALIDATE (reference TODO, main.zig:199) makes it one.
+    cut = bytes([1, 0, 0, 0, 9, 65, 1, 0b10000000, 66, 1])
+    n, out = codec.decode(cut)
+    assert n == 0 and out.size == 0
+    with pytest.raises(et.EntreepyError) as e:
+        codec.decode(cut, et.DecodeFlags(write_output=True, validate=True))
+    assert e.value.name == "Corrupt"
+
+
+def test_single_symbol_round_trip_is_the_reference_s(codec):
+    # one distinct symbol: the root is a leaf, the code has length 0, the dictionary is empty (encode.zig:204-212,
+    # 270-275) and the file is 9 bytes; the reference decoder reads back 0 bytes without an error (decode.zig:66)
+    data = np.full(1000, 97, dtype=np.uint8)
+    n, enc = codec.encode(data)
+    assert n == 9 and enc.tobytes() == oracle.encode(data).tobytes()
+    m, out = codec.decode(enc[4:n])
+    assert m == 0 and out.size == 0
+    assert codec.decode(enc[4:n], et.DecodeFlags(write_output=True, validate=True))[0] == 0
+
+
+def _dict_stream(entries, body_len, body):
+    """file[4..] for a hand-made dictionary: entries = [(symbol, length, code)]."""
+    bits = []
+    for sym, length, code in entries:
+        bits += [(sym >> (7 - k)) & 1 for k in range(8)] + [(length >> (7 - k)) & 1 for k in range(8)]
+        bits += [(code >> (length - 1 - k)) & 1 for k in range(length)]
+    bits += [0] * (-len(bits) % 8)
+    d = np.packbits(np.array(bits, dtype=np.uint8)).tobytes()
+    return bytes([len(entries) - 1]) + int(body_len).to_bytes(4, "big") + d + bytes(body)
+
+
+def test_validate_flag_and_reference_acceptance(codec):
+    strict = et.DecodeFlags(write_output=True, validate=True)
+    # a = 0, b = 01 (a is a prefix of b): the reference tries lengths from the shortest up (decode.zig:175-181), so
+    # b can never match; body 0 1 0 0 ... decodes as a, then "1" is no code
+    stream = _dict_stream([(97, 1, 0b0), (98, 2, 0b01)], 3, [0b00000000])
+    n, out = codec.decode(stream)
+    assert out.tobytes() == b"aaa"
+    with pytest.raises(et.EntreepyError) as e:
+        codec.decode(stream, strict)
+    assert e.value.name == "Corrupt"
+    # a repeated (length, code): the later entry overwrites the earlier one (decode.zig:123-125)
+    stream = _dict_stream([(97, 1, 0b0), (98, 1, 0b1), (99, 1, 0b1)], 4, [0b01010000])
+    assert codec.decode(stream)[1].tobytes() == b"acac"
     with pytest.raises(et.EntreepyError):
-        codec.decode(bytes([1, 0, 0, 0, 9, 65, 1, 0b10000000, 66, 1]))  # second entry truncated
+        codec.decode(stream, strict)
+    # incomplete code (Kraft sum 3/4): accepted as long as the body only uses what exists; rejected when validated
+    stream = _dict_stream([(97, 1, 0b0), (98, 2, 0b10)], 3, [0b01000000])
+    assert codec.decode(stream)[1].tobytes() == b"aba"
+    with pytest.raises(et.EntreepyError):
+        codec.decode(stream, strict)
+    # body too short for body_len symbols
+    good = oracle.encode(np.frombuffer(b"abracadabra" * 30, dtype=np.uint8)).tobytes()[4:]
+    assert codec.decode(good, strict)[1].tobytes() == b"abracadabra" * 30
+    with pytest.raises(et.EntreepyError):
+        codec.decode(good[:-40], strict)
+
+
+def test_fixed_length_codes_take_closed_form_entries(codec):
+    # 2^k equiprobable symbols: every code has k bits, a wrong parse never re-synchronises (k = 3, 5, 6, 7 do not
+    # divide the 128-bit run-up).  The entries follow from the first one in closed form: no repair rounds.
+    import torch
+
+    rng = np.random.default_rng(31)
+    for k, n in ((7, (64 << 20) + 5), (3, (64 << 20) + 1), (5, 3_000_001), (6, 70001), (1, 100003), (2, 1 << 20)):
+        syms = torch.from_numpy(rng.permutation(256)[: 1 << k].astype(np.uint8)).cuda()
+        g = torch.Generator(device="cuda")
+        g.manual_seed(k)
+        text = syms[torch.randint(0, 1 << k, (n,), generator=g, device="cuda")].contiguous()  # near-equal counts: a full tree
+        torch.cuda.synchronize()
+        enc = torch.empty(n + 8192, dtype=torch.uint8, device="cuda")
+        size = codec.encode_dev(text.data_ptr(), n, enc.data_ptr(), enc.numel(), et._abi.FLAG_WRITE_OUTPUT | et._abi.FLAG_NO_SCRATCH_LIMIT)
+        d = et.parse_header(enc[4:4 + 2048].cpu().numpy())
+        assert d.min_length == d.max_length == k
+        dec = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        got = codec.decode_dev(enc.data_ptr() + 4, size - 4, dec.data_ptr(), n)
+        assert got == n and torch.equal(dec, text), k
+        assert codec.last_decode_rounds <= 2, (k, codec.last_decode_rounds)
 
 
 def test_round_trip_text_16m_property(codec, manifest):

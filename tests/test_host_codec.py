@@ -96,11 +96,26 @@ def test_parse_header_round_trips_the_dictionary(golden_et, fixtures):
         assert [d.symbol[e] for e in range(d.n_entries)] == sorted(d.symbol[e] for e in range(d.n_entries))
 
 
-def test_parse_header_rejects_truncated_streams(golden_et):
+def test_parse_header_on_truncated_streams_follows_the_reference(golden_et):
     et_file = golden_et["nice.shakespeare.txt"][4:]
-    for cut in (0, 3, 5, 20, 60):
+    for cut in (0, 3):  # decode.zig:36-42 reads compressed_text[1..4]: out of bounds
         with pytest.raises(et.EntreepyError):
             et.parse_header(et_file[:cut])
+    whole = et.parse_header(et_file)
+    assert not whole.truncated
+    # the dictionary state machine stops when the bytes run out (decode.zig:66): what was read stands, the body is empty
+    for cut in (5, 20, 60):
+        d = et.parse_header(et_file[:cut])
+        assert d.truncated and d.n_entries < whole.n_entries and d.body_offset == cut and d.body_len == whole.body_len
+        for e in range(d.n_entries):
+            assert (d.symbol[e], d.length[e], d.code[e]) == (whole.symbol[e], whole.length[e], whole.code[e])
+
+
+def test_single_symbol_file_parses_to_an_empty_dictionary():
+    enc = oracle.encode(np.full(1000, 7, dtype=np.uint8)).tobytes()
+    assert len(enc) == 9  # encode.zig:270-275: zero entries
+    d = et.parse_header(enc[4:])
+    assert d.n_entries == 0 and d.truncated and d.body_len == 1000 and d.body_offset == 5
 
 
 def test_no_cpu_fallback_without_a_device():
