@@ -183,7 +183,8 @@ extern "C" int et_parse_header(const uint8_t *in, size_t n, et_dictionary *dict)
         // read so far stand and the body is empty, so nothing is decoded and no error is raised.  This is also how
         // its own output for a single distinct symbol reads back (9-byte file, zero entries, encode.zig:270-275).
         bool whole = src.take(8, &sym) && src.take(8, &len);
-        if (whole && len > 64) return ET_ERR_UNSUPPORTED;
+        if (whole && src.at + len > src.nbits) whole = false;  // the code bits are not all there: the reference stops reading
+        if (whole && len > 64) return ET_ERR_UNSUPPORTED;      // (the reference's [32]u8 entry is indexed out of bounds, decode.zig:124)
         whole = whole && src.take((unsigned)len, &code);
         if (!whole) {
             dict->n_entries = e;

@@ -331,11 +331,13 @@ class ShardedCodec:
         cuts, ranges = self.decode_ranges(body_bytes)
         s, t = ranges[p.rank]
         own_begin, own_end = cuts[p.rank] - s, cuts[p.rank + 1] - s
-        head_bit = 0 if p.rank == 0 else -1
+        head_bit = 0 if cuts[p.rank] == 0 else -1  # a share that begins with the body begins on a codeword
         rounds, redo = 0, True
         n = entry = exit_ = 0
         while True:
-            if redo:
+            if redo and own_begin == own_end:  # an empty share (short bodies give the later cuts nothing): no kernel to run
+                n, entry, exit_ = 0, own_begin * 8, own_end * 8
+            elif redo:
                 n, entry, exit_ = be.unpack_shard(t_range, t - s, own_begin, own_end, dictionary, head_bit, t_out)   # K3-K5
             rounds += 1
             if p.world == 1:

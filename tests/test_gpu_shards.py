@@ -29,8 +29,15 @@ def _oracle_et(data):
 
 
 def _text(n, seed=5):
-    rng = np.random.default_rng(seed)
-    return rng.choice(np.frombuffer(b"etaoin shrdlu\n,.", dtype=np.uint8), n)
+    """English-frequency text (code lengths 3..17: shard bit offsets take every phase)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    man = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+    thr = synth.thresholds_from_weights(synth.text_weights(man["midsummer_histogram"]))
+    return synth.generate(n, thr, seed=synth.SEED + seed)
 
 
 def _fib32():
