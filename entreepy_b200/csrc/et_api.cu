@@ -274,6 +274,7 @@ extern "C" void et_ctx_destroy(et_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    unpack_free_device(&ctx->tune);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_small) cudaFree(ctx->d_small);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -307,6 +308,7 @@ extern "C" int et_ctx_set_tuning(et_ctx *ctx, int key, long long value) {
     switch (key) {
         case ET_TUNE_LANE_MIN_BYTES: ctx->tune.lane_min_bytes = value; return ET_OK;
         case ET_TUNE_DEBUG: ctx->tune.debug = value != 0; return ET_OK;
+        case ET_TUNE_SYNC_WARPS: ctx->tune.sync_warps = (int)value; return ET_OK;
     }
     return fail(ctx, ET_ERR_INVALID_ARG, "unknown tuning key %d", key);
 }

@@ -76,8 +76,11 @@ struct UnpackTuning {
     int debug = 0;
     int max_smem = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int num_sms = 0;
+    int sync_warps = 0;             // > 0: warps per CTA of the count walk (default: as many as fit)
+    void *d_lane_tables = nullptr;  // device-built tables of the lane-interleaved decoder
 };
 cudaError_t unpack_init_device(int device, UnpackTuning *tune);
+void unpack_free_device(UnpackTuning *tune);
 
 // Chunk size for this stream (bytes per thread) and the device scratch the decoder needs.
 uint32_t unpack_chunk_bytes(const UnpackGeometry &g, const UnpackTuning &tune, uint32_t min_length, uint32_t max_length);

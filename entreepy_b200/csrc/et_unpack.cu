@@ -56,6 +56,9 @@ struct DecArgs {
     const uint32_t *wlut;
     const uint32_t *nodes;
     const uint16_t *slots;        // slot of every marker window (kLutSize), then the second-level tables
+    const uint16_t *t_count;      // lane-interleaved decoder: device-built tables (lane_tables_kernel)
+    const uint32_t *t_write;
+    const uint8_t *t_single;
     uint16_t *start_off;          // [n] first codeword of the chunk, bits past the chunk's first bit
     uint16_t *exit_off;           // [n] first codeword boundary at or after the chunk's end, bits past that end
     uint32_t *count;              // [n] symbols that begin inside the chunk
@@ -69,6 +72,7 @@ struct DecArgs {
     uint32_t *error_flags;
     unsigned long long *total;
     uint32_t *entry_exit;
+    unsigned long long *dbg;      // ET_TUNE_DEBUG: per CTA {smid, start ns, end ns} of the two big lane kernels (or null)
     uint8_t *out;
     uint64_t max_symbols;
 };
@@ -605,724 +609,7 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
     if (bad) atomicOr(a.error_flags, kErrInvalidCode);
 }
 
-// ====================================================================== lane-interleaved decoder
-// The fast path for long streams whose code re-synchronises quickly.  Same protocol as above
-// (run-up from a guess, repair rounds, fixpoint check, scan, write walk) but the unit of work
-// is a REGION: 32 consecutive chunks of 33 stream words, one warp per region, one lane per chunk.
-//   * the region (plus 16 bytes either side) is brought into shared memory by coalesced 16-byte
-//     loads and byte-swapped once on the way in.  A chunk is 33 words, so lane L reads image word
-//     33 L + j: bank (L + j) mod 32 — lanes at the same depth of their chunks never conflict;
-//   * the walk is ONE flat loop: two table lookups, then at most one 32-bit refill of a 64-bit
-//     window (a lookup consumes at most 12 bits, so two always fit).  The lanes of a warp meet
-//     again only at the end of the chunk, not at every stream word as the per-thread walkers
-//     above must (their words live in registers and cannot be indexed dynamically);
-//   * the write walk assembles the text of the whole region in shared memory at its final
-//     relative position (the chunks of a region are consecutive in the text as well), four
-//     symbols per shared store, and the warp copies it out as aligned 16-byte vectors: no
-//     partly written sector ever reaches L2 except at the two ends of a region.
-constexpr uint32_t kLaneWords = 33;
-constexpr uint32_t kLaneBytes = kLaneWords * 4;
-constexpr uint32_t kSplitWords = 17;  // the write walk decodes words [0, 17) and [17, 33) of a chunk side by side
-constexpr uint32_t kRegionBytes = 32 * kLaneBytes;            // 4224 = 33 lines of 128 bytes
-constexpr uint32_t kImgBytes = 16 + kRegionBytes + 16;        // run-up of lane 0 | region | look-ahead of lane 31
-constexpr uint32_t kRunupWords = 4;
-constexpr int kSyncWarps = 16;
-constexpr uint32_t kSubBytes = (kMaxSubTables << kSubBits) * 2;   // second-level tables in shared memory
-constexpr uint32_t kTableBytes = kLutSize * 4 + kSubBytes;
-constexpr uint32_t kSyncSmem = kTableBytes + kSyncWarps * kImgBytes;
-
-struct BitBuf {
-    uint32_t hi, lo, nxt;  // three consecutive stream words; the window is cut from hi:lo
-    uint32_t addr;         // shared address of the word after nxt
-};
-__device__ __forceinline__ void buf_open(BitBuf &b, uint32_t addr0) {
-    b.hi = lds_u32(addr0);
-    b.lo = lds_u32(addr0 + 4);
-    b.nxt = lds_u32(addr0 + 8);
-    b.addr = addr0 + 12;
-}
-__device__ __forceinline__ void buf_shift(BitBuf &b) {
-    b.hi = b.lo;
-    b.lo = b.nxt;
-    b.nxt = lds_u32(b.addr);
-    b.addr += 4;
-}
-// Top 32 bits of (hi:lo) << pos, pos < 64 (one funnel shift on the 64-bit pair).
-__device__ __forceinline__ uint32_t window64(const BitBuf &b, uint32_t pos) {
-    return (uint32_t)(((((uint64_t)b.hi << 32) | b.lo) << (pos & 63u)) >> 32);
-}
-// One code longer than the first-level window at bit pos (< 32) of hi:lo.  slot_e: the marker's
-// second-level slot (0x8000 | slot) or kNoSlot; sub_s: shared address of the second-level tables.
-// Returns the code's length, 0 = no such code.
-__device__ __forceinline__ uint32_t long_code_at(const BitBuf &b, uint32_t pos, uint32_t slot_e, uint32_t sub_s,
-                                                 const DecArgs &a, uint32_t *sym) {
-    const uint32_t win = __funnelshift_l(b.lo, b.hi, pos);
-    if (slot_e != kNoSlot) {
-        const uint32_t se = lds_tab_u16(sub_s + ((slot_e & (kMaxSubTables - 1)) << (kSubBits + 1)) +
-                                    ((win >> (31 - kLutBits - kSubBits)) & ((1u << (kSubBits + 1)) - 2u)));
-        if (se) {
-            *sym = se & 0xffu;
-            return se >> 8;
-        }
-    }
-    return long_code(win, __ldg(a.wlut + (win >> (32 - kLutBits))) & 0xffffu, a.nodes, sym);
-}
-// Byte offset of the table entry (32 bit) for the window at bit pos (< 64) of hi:lo.
-__device__ __forceinline__ uint32_t entry_offset(const BitBuf &b, uint32_t pos) {
-    return (window64(b, pos) >> (30 - kLutBits)) & ((kLutSize - 1) << 2);
-}
-
-// Count walk over `nwords` stream words whose first word is at shared address addr0, starting at
-// bit pos0 (< 32) of that word.  Consumes every symbol that begins before the end of the last
-// word.  Returns the symbol count; *exit_bits = bits past that end at which the walk stopped.
-// Walk state c: bits 0-6 position relative to b.hi (below 64 inside the main loop, up to 95 at the
-// very end), bits 9+ symbols.  Table entries (32 bit, shared): low half = bits consumed |
-// symbols << 9 for every whole code in the window, 0 = the first code is longer than the window
-// (the state does not move; the second lookup of a pair then reads 0 as well); high half = the
-// same for the first code alone, or for a marker 0x8000 | second-level slot / kNoSlot.
-__device__ __forceinline__ uint32_t lane_count(uint32_t addr0, uint32_t nwords, uint32_t pos0, uint32_t clut_s, uint32_t sub_s,
-                                               const DecArgs &a, uint32_t *exit_bits) {
-    BitBuf b;
-    buf_open(b, addr0);
-    uint32_t c = pos0;
-    const uint32_t limit = addr0 + 4u * (nwords + 1u);  // b.addr == limit: hi:lo are the last two words
-    while (b.addr < limit) {
-        c += lds_tab_u16(clut_s + entry_offset(b, c));
-        const uint32_t e2 = lds_tab_u16(clut_s + entry_offset(b, c));
-        c += e2;
-        if (e2 == 0) {  // rare: a code of more than 12 bits
-            if (c & 32u) {
-                buf_shift(b);
-                c -= 32u;
-            }
-            uint32_t sym;
-            const uint32_t len = long_code_at(b, c & 31u, lds_tab_u16(clut_s + entry_offset(b, c) + 2u), sub_s, a, &sym);
-            c += len ? (len | (1u << 9)) : 1u;
-        }
-        if (c & 32u) {
-            buf_shift(b);
-            c -= 32u;
-        }
-    }
-    // the last words: hi:lo end 64 or 32 bits short of the chunk's end (32: a long code crossed a word at the very end)
-    uint32_t end_rel = 32u * (nwords + 3u) - 8u * (b.addr - addr0);
-    while ((c & 127u) + kLutBits <= end_rel) {  // whole windows that cannot cross the end
-        const uint32_t e = lds_tab_u16(clut_s + entry_offset(b, c));
-        if (e == 0) break;
-        c += e;
-    }
-    for (;;) {  // one symbol at a time up to the end
-        if ((c & 127u) >= end_rel) break;
-        if (c & 32u) {
-            buf_shift(b);
-            c -= 32u;
-            end_rel -= 32u;
-        }
-        uint32_t add = lds_tab_u16(clut_s + entry_offset(b, c) + 2u);
-        if (add & 0x8000u) {
-            uint32_t sym;
-            const uint32_t len = long_code_at(b, c & 31u, add, sub_s, a, &sym);
-            add = len ? (len | (1u << 9)) : 1u;
-        }
-        c += add;
-    }
-    *exit_bits = (c & 127u) - end_rel;
-    return c >> 9;
-}
-
-// Coalesced copy of a region's stream bytes (and 16 either side) into the warp's shared image,
-// big-endian words swapped to native.  Split in two so that the loads of the NEXT region can be
-// in flight (in registers) while the warp walks the current one.
-constexpr uint32_t kImgVecs = kImgBytes / 16;            // 266
-constexpr uint32_t kImgVecsPerLane = (kImgVecs + 31) / 32;  // 9
-struct RegionRegs {
-    uint4 v[kImgVecsPerLane];
-};
-__device__ __forceinline__ void region_load(const DecArgs &a, uint64_t region_byte, uint32_t lane, RegionRegs &q) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.body_aligned + region_byte - 16);
-#pragma unroll
-    for (uint32_t i = 0; i < kImgVecsPerLane; ++i)
-        if (i * 32 + lane < kImgVecs) q.v[i] = ld_stream_v4(src + i * 32 + lane);
-}
-__device__ __forceinline__ void region_store(const RegionRegs &q, uint32_t img_s, uint32_t lane) {
-#pragma unroll
-    for (uint32_t i = 0; i < kImgVecsPerLane; ++i)
-        if (i * 32 + lane < kImgVecs) {
-            const uint4 w = swap4(q.v[i]);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(img_s + (i * 32 + lane) * 16), "r"(w.x), "r"(w.y),
-                         "r"(w.z), "r"(w.w)
-                         : "memory");
-        }
-}
-__device__ __forceinline__ void region_prefetch_l2(const DecArgs &a, uint64_t region_byte, uint32_t lane) {
-    const uint8_t *p = a.body_aligned + region_byte + (uint64_t)lane * 128;  // 33 lines; the last one rides on lane 0's neighbour
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32 * 128));
-}
-
-struct Region {
-    uint64_t begin_byte;  // first byte of the region (16-byte aligned offset from body_aligned)
-    bool interior;        // the whole image is plain readable stream owned by this call, and it is not region 0
-};
-__device__ __forceinline__ Region region_of(const DecArgs &a, uint32_t r) {
-    Region g;
-    g.begin_byte = (a.grid_bit >> 3) + (uint64_t)r * kRegionBytes;
-    const uint64_t end_byte = g.begin_byte + kRegionBytes;
-    g.interior = r > 0 && end_byte * 8 <= a.own_end_bit && end_byte * 8 + 128 <= a.end_bit && end_byte + 16 <= a.byte_hi &&
-                 g.begin_byte >= a.byte_lo + 16;
-    return g;
-}
-
-// ------------------------------------------------------------------ the ends of the stream
-// Regions that touch the ends of the stream (the first one, the last ones) are staged with guarded
-// loads — bytes outside the readable range read as zero — and their chunks are walked from the
-// same shared image.  A chunk that lies wholly inside the owned stream with at least 32 bits of
-// stream after it takes the fast walkers like any other; the others (the last chunk of the
-// stream, a first chunk whose known start is not in its first word) are walked one symbol at a
-// time with every limit checked, from the shared tables.
-__device__ __forceinline__ void region_stage_guarded(const DecArgs &a, uint64_t region_byte, uint32_t img_s, uint32_t lane) {
-    for (uint32_t v = lane; v < kImgVecs; v += 32) {
-        const long long byte = (long long)region_byte - 16 + 16ll * v;  // region 0 starts at byte 0: its run-up is not stream
-        uint4 w = make_uint4(0, 0, 0, 0);
-        if (byte >= (long long)a.byte_lo && byte + 16 <= (long long)a.byte_hi) {
-            w = swap4(ld_stream_v4(a.body_aligned + byte));
-        } else if (byte + 16 > (long long)a.byte_lo && byte < (long long)a.byte_hi) {
-            const long long lo = (long long)a.byte_lo - byte, hi = (long long)a.byte_hi - byte;
-            w = swap4(ld_partial_v4(a.body_aligned + byte, (int)(lo > 0 ? lo : 0), (int)(hi < 16 ? hi : 16)));
-        }
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(img_s + v * 16), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-    }
-}
-
-struct LaneGeom {
-    uint32_t own_bits;   // symbols that begin in the first own_bits bits of the chunk are this chunk's (1056 unless the owned stream ends inside)
-    uint32_t hard_bits;  // no code may extend past this bit of the chunk (the end of the stream), clamped
-    bool fast;           // whole chunk owned and far enough from the end of the stream for the fast walkers
-    bool runup;          // the 128 bits before the chunk are stream
-};
-__device__ __forceinline__ LaneGeom lane_geom(const DecArgs &a, uint32_t gc) {
-    LaneGeom l;
-    const uint64_t begin = a.grid_bit + (uint64_t)gc * (kLaneBytes * 8);
-    const uint64_t own = a.own_end_bit > begin ? a.own_end_bit - begin : 0, hard = a.end_bit > begin ? a.end_bit - begin : 0;
-    l.own_bits = own < kLaneBytes * 8 ? (uint32_t)own : kLaneBytes * 8;
-    l.hard_bits = hard < 4096 ? (uint32_t)hard : 4096u;
-    l.fast = l.own_bits == kLaneBytes * 8 && l.hard_bits >= kLaneBytes * 8 + 32;
-    l.runup = begin >= a.byte_lo * 8 + 32 * kRunupWords;
-    return l;
-}
-
-// One symbol at bit `pos` of the chunk whose first word is at shared address chunk_s.  single_add: the
-// first-code half of the count table's entry layout (length | 1 << 9, or a marker).  Returns the code's
-// length (0 = no code here).
-__device__ __forceinline__ uint32_t edge_symbol(uint32_t chunk_s, uint32_t pos, uint32_t clut_s, uint32_t sub_s, const DecArgs &a,
-                                                uint32_t *sym, bool want_sym, uint32_t wlut_s) {
-    BitBuf b;
-    b.hi = lds_u32(chunk_s + 4u * (pos >> 5));
-    b.lo = lds_u32(chunk_s + 4u * (pos >> 5) + 4u);
-    b.nxt = 0;
-    b.addr = 0;
-    const uint32_t off = entry_offset(b, pos & 31u);
-    if (want_sym) {
-        const uint32_t e = lds_u32(wlut_s + off);
-        if (e >= 0x10000u) {
-            *sym = e & 0xffu;
-            return (e >> 23) & 15u;
-        }
-        return long_code_at(b, pos & 31u, e, sub_s, a, sym);
-    }
-    const uint32_t add = lds_u16(clut_s + off + 2u);
-    if (!(add & 0x8000u)) return add & 0x3fu;
-    return long_code_at(b, pos & 31u, add, sub_s, a, sym);
-}
-// Count walk with every limit checked (same rules as walk_generic).
-__device__ __noinline__ uint32_t lane_count_edge(uint32_t chunk_s, uint32_t start, const LaneGeom &l, uint32_t clut_s, uint32_t sub_s,
-                                                 const DecArgs &a, uint32_t *exit_bits) {
-    uint32_t pos = start, cnt = 0;
-    while (pos < l.own_bits) {
-        uint32_t sym;
-        const uint32_t len = edge_symbol(chunk_s, pos, clut_s, sub_s, a, &sym, false, 0);
-        if (len == 0) {  // no code here (incomplete dictionary): skip one bit, like every other walker
-            pos += 1;
-            continue;
-        }
-        if (pos + len > l.hard_bits) break;  // final pad bits look like the start of a longer code
-        pos += len;
-        cnt += 1;
-    }
-    *exit_bits = pos > l.own_bits ? pos - l.own_bits : 0u;
-    return cnt;
-}
-
-// Which regions hold a chunk whose recorded entry is not its left neighbour's recorded exit?  One warp looks at
-// four regions; the list it leaves is the work of the next repair round.
-__global__ void __launch_bounds__(256) region_check_kernel(const DecArgs a, uint32_t n_regions) {
-    const uint32_t lane = threadIdx.x & 31, w = (blockIdx.x * 256 + threadIdx.x) >> 5;
-    bool bad[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t r = w * 4 + k, gc = r * 32 + lane;
-        bad[k] = r < n_regions && gc > 0 && gc < a.n_chunks && a.exit_off[gc - 1] != a.start_off[gc];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (__any_sync(0xffffffffu, bad[k]) && lane == 0) {
-            a.work[atomicAdd(a.work_count, 1u)] = w * 4 + k;
-            *a.changed = 1u;
-        }
-}
-
-// Persistent: grid = resident CTAs, every warp strides over the regions (round 0) or over the list
-// region_check_kernel left (repair rounds); the tables are filled once per CTA.
-__global__ void __launch_bounds__(kSyncWarps * 32, 2) region_sync_kernel(const DecArgs a, uint32_t n_regions, int round) {
-    extern __shared__ __align__(16) uint8_t dyn[];  // count table | second-level tables | one stream image per warp
-    uint32_t *clut_sh = reinterpret_cast<uint32_t *>(dyn);
-    uint16_t *sub_sh = reinterpret_cast<uint16_t *>(dyn + kLutSize * 4);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t stride = gridDim.x * kSyncWarps;
-    const uint32_t n_items = round == 0 ? n_regions : *a.work_count;
-    if (blockIdx.x * kSyncWarps >= n_items) return;  // repair rounds: usually only a few CTAs have anything to do
-    for (int i = threadIdx.x; i < kLutSize; i += kSyncWarps * 32) {
-        const uint32_t e = a.clut[i];
-        clut_sh[i] = (e & kLutMarker) ? ((uint32_t)(a.slots[i] == kNoSlot ? kNoSlot : (0x8000u | a.slots[i])) << 16) : e;
-    }
-    for (uint32_t i = threadIdx.x; i < kSubBytes / 2; i += kSyncWarps * 32) sub_sh[i] = a.slots[kLutSize + i];
-    __syncthreads();
-    const uint32_t clut_s = pinned(smem_addr(clut_sh)), sub_s = pinned(smem_addr(sub_sh));
-    const uint32_t img_s = pinned(smem_addr(dyn) + kTableBytes + warp * kImgBytes);
-    for (uint32_t item = blockIdx.x * kSyncWarps + warp; item < n_items; item += stride) {
-        const uint32_t r = round == 0 ? item : a.work[item];
-        const uint32_t gc = r * 32 + lane;
-        uint32_t start = 0;
-        bool work = gc < a.n_chunks;
-        if (work && round != 0) {
-            if (gc == 0) {
-                work = false;
-            } else {
-                start = a.exit_off[gc - 1];
-                work = start != a.start_off[gc];
-            }
-        }
-        if (!__any_sync(0xffffffffu, work)) continue;
-        if (gc == 0 && a.head_known) start = a.head_off;
-        const bool known = round != 0 || (gc == 0 && a.head_known);
-        const Region g = region_of(a, r);
-        uint32_t cnt = 0, entry = start, exit_bits = 0;
-        if (g.interior) {
-            RegionRegs q;
-            region_load(a, g.begin_byte, lane, q);
-            if (round == 0 && r + stride < n_regions) region_prefetch_l2(a, g.begin_byte + (uint64_t)stride * kRegionBytes, lane);
-            __syncwarp();  // the walk of the region before this one has left the image
-            region_store(q, img_s, lane);
-            __syncwarp();
-            if (work) {
-                const uint32_t chunk_s = img_s + 16 + lane * kLaneBytes;
-                if (!known) {
-                    uint32_t e;
-                    (void)lane_count(chunk_s - 4 * kRunupWords, kRunupWords, 0u, clut_s, sub_s, a, &e);
-                    entry = e;
-                }
-                uint32_t mid_bits;
-                const uint32_t cnt_a = lane_count(chunk_s, kSplitWords, entry, clut_s, sub_s, a, &mid_bits);
-                cnt = cnt_a + lane_count(chunk_s + 4 * kSplitWords, kLaneWords - kSplitWords, mid_bits, clut_s, sub_s, a, &exit_bits);
-                a.mid[gc] = mid_bits | (cnt_a << 16);
-            }
-        } else {
-            __syncwarp();
-            region_stage_guarded(a, g.begin_byte, img_s, lane);
-            __syncwarp();
-            if (work) {
-                const LaneGeom l = lane_geom(a, gc);
-                const uint32_t chunk_s = img_s + 16 + lane * kLaneBytes;
-                if (!known && l.runup) {
-                    uint32_t e;
-                    (void)lane_count(chunk_s - 4 * kRunupWords, kRunupWords, 0u, clut_s, sub_s, a, &e);
-                    entry = e;
-                }
-                if (l.fast && entry < 32u) {
-                    uint32_t mid_bits;
-                    const uint32_t cnt_a = lane_count(chunk_s, kSplitWords, entry, clut_s, sub_s, a, &mid_bits);
-                    cnt = cnt_a + lane_count(chunk_s + 4 * kSplitWords, kLaneWords - kSplitWords, mid_bits, clut_s, sub_s, a, &exit_bits);
-                    a.mid[gc] = mid_bits | (cnt_a << 16);
-                } else {
-                    cnt = lane_count_edge(chunk_s, entry, l, clut_s, sub_s, a, &exit_bits);
-                }
-            }
-        }
-        if (work) {
-            a.start_off[gc] = (uint16_t)entry;
-            a.exit_off[gc] = (uint16_t)exit_bits;
-            a.count[gc] = cnt;
-        }
-    }
-}
-
-// Scan of the symbols per region, three small kernels: sums of every region and of every group
-// of 1024 regions (plus the largest region: it sizes the text stage of a warp); one-block scan of
-// the group sums (chunk_scan_kernel); scan inside every group.
-constexpr uint32_t kGroupRegions = 1024;
-__global__ void __launch_bounds__(1024) region_sum_kernel(const DecArgs a, uint32_t n_regions) {
-    __shared__ uint32_t warp_sum[32], warp_max[32];
-    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t r0 = blockIdx.x * kGroupRegions + warp * 32;
-    uint32_t mine = 0;  // lane k keeps the sum of region r0 + k
-    for (uint32_t k = 0; k < 32; ++k) {
-        const uint32_t gc = (r0 + k) * 32 + lane;
-        uint32_t v = (r0 + k < n_regions && gc < a.n_chunks) ? a.count[gc] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == k) mine = v;
-    }
-    if (r0 + lane < n_regions) a.block_prefix[r0 + lane] = mine;
-    uint32_t sum = mine, big = mine;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        big = max(big, __shfl_xor_sync(0xffffffffu, big, o));
-    }
-    if (lane == 0) {
-        warp_sum[warp] = sum;
-        warp_max[warp] = big;
-    }
-    __syncthreads();
-    if (t == 0) {
-        unsigned long long s = 0;
-        uint32_t m = 0;
-        for (int i = 0; i < 32; ++i) {
-            s += warp_sum[i];
-            m = max(m, warp_max[i]);
-        }
-        a.group_prefix[blockIdx.x] = s;
-        atomicMax(a.max_sum, m);
-    }
-}
-__global__ void __launch_bounds__(1024) region_apply_kernel(const DecArgs a, uint32_t n_regions) {
-    __shared__ uint32_t warp_sum[32];
-    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t r = blockIdx.x * kGroupRegions + t;
-    const uint32_t v = r < n_regions ? (uint32_t)a.block_prefix[r] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += up;
-    }
-    if (lane == 31) warp_sum[warp] = incl;
-    __syncthreads();
-    uint32_t before = 0;
-    for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
-    if (r < n_regions) a.block_prefix[r] = a.group_prefix[blockIdx.x] + before + (incl - v);
-}
-
-// ------------------------------------------------------------------ write walk of a lane
-struct OutAcc {
-    uint32_t lo, hi;  // the last 8 symbols, newest in the top byte of hi
-    uint32_t A;       // shared address of the next text byte
-};
-// Append the `sh`/8 symbols in the low bytes of `syms` (sh = 0, 8 or 16).  When the text address
-// crosses a multiple of 4 the finished word is stored (one symbol of the next word may already
-// sit on top of it).  A lane's first word may hold bytes of the lane before it: those are
-// rewritten by that lane's lane_flush() after the warp has met.
-__device__ __forceinline__ void emit(OutAcc &r, uint32_t syms, uint32_t sh) {
-    r.lo = __funnelshift_r(r.lo, r.hi, sh);
-    r.hi = __funnelshift_r(r.hi, syms, sh);
-    const uint32_t a2 = r.A + (sh >> 3);
-    if ((r.A ^ a2) & 4u) sts_u32((a2 & ~3u) - 4u, __funnelshift_l(r.lo, r.hi, a2 << 3));
-    r.A = a2;
-}
-// The same for the symbols of two table entries at once (up to four symbols, 8 x symbols in the top
-// five bits of either entry): at most one word is completed.
-__device__ __forceinline__ void emit_pair(OutAcc &r, uint32_t e1, uint32_t e2) {
-    const uint32_t s1 = e1 >> 27, s12 = s1 + (e2 >> 27);
-    const uint32_t syms = (e1 & 0xffffu) | (e2 << s1);  // bits of e2 above its symbols land above the 8 x (symbols) bits that are used
-    r.lo = __funnelshift_rc(r.lo, r.hi, s12);
-    r.hi = __funnelshift_rc(r.hi, syms, s12);
-    const uint32_t a2 = r.A + (s12 >> 3);
-    if ((r.A ^ a2) & 4u) sts_u32((a2 & ~3u) - 4u, __funnelshift_l(r.lo, r.hi, a2 << 3));
-    r.A = a2;
-}
-// The bytes after the lane's last whole word (at most 3, never before a_begin), one at a time.
-__device__ __forceinline__ void lane_flush(const OutAcc &r, uint32_t a_begin) {
-    uint32_t k = r.A & 3u;
-    if (r.A - a_begin < k) k = r.A - a_begin;
-    for (uint32_t i = 0; i < k; ++i) {
-        const uint32_t byte = (r.hi >> (8u * (4u - k + i))) & 0xffu;
-        asm volatile("st.shared.u8 [%0], %1;" ::"r"(r.A - k + i), "r"(byte) : "memory");
-    }
-}
-
-// Table entries of the write walk (32 bit, shared): symbols (one or two) in bits 0-15, bits consumed
-// in 16-21, length of the first code in 23-26, 8 x symbols in 27-31.  A marker (first code longer
-// than the window) is 0x8000 | second-level slot or kNoSlot: nothing consumed, nothing appended.
-// Walk state c: bits 0-6 position relative to b.hi, the rest is noise from the adds.
-struct WriteWalk {
-    BitBuf b;
-    uint32_t c, addr0, limit;
-    OutAcc r;
-};
-__device__ __forceinline__ void walk_open(WriteWalk &w, uint32_t addr0, uint32_t nwords, uint32_t pos0, uint32_t text_s) {
-    buf_open(w.b, addr0);
-    w.c = pos0;
-    w.addr0 = addr0;
-    w.limit = addr0 + 4u * (nwords + 1u);  // b.addr == limit: hi:lo are the last two words
-    w.r.lo = w.r.hi = 0;
-    w.r.A = text_s;
-}
-__device__ __forceinline__ void walk_refill(WriteWalk &w) {
-    if (w.c & 32u) {
-        buf_shift(w.b);
-        w.c -= 32u;
-    }
-}
-// The lookup before this did not move: a code of more than 12 bits (or no code at all).
-__device__ __forceinline__ void walk_long(WriteWalk &w, uint32_t wlut_s, uint32_t sub_s, const DecArgs &a, uint32_t *bad) {
-    walk_refill(w);
-    uint32_t sym = 0;
-    const uint32_t len = long_code_at(w.b, w.c & 31u, lds_tab_u32(wlut_s + entry_offset(w.b, w.c)), sub_s, a, &sym);
-    if (len) {
-        w.c += len;
-        emit(w.r, sym, 8u);
-    } else {
-        *bad = 1u;
-        w.c += 1u;
-    }
-}
-// Two lookups, then at most one refill (a lookup consumes at most 12 bits).
-__device__ __forceinline__ void walk_pair(WriteWalk &w, uint32_t wlut_s, uint32_t sub_s, const DecArgs &a, uint32_t *bad) {
-    const uint32_t e1 = lds_tab_u32(wlut_s + entry_offset(w.b, w.c));
-    w.c += e1 >> 16;
-    const uint32_t e2 = lds_tab_u32(wlut_s + entry_offset(w.b, w.c));
-    w.c += e2 >> 16;
-    emit_pair(w.r, e1, e2);
-    if (e2 < 0x10000u) walk_long(w, wlut_s, sub_s, a, bad);
-    walk_refill(w);
-}
-// Whatever is left of the main loop, then the last words: whole windows while they cannot cross
-// the end, then one symbol at a time.
-__device__ __forceinline__ void walk_finish(WriteWalk &w, uint32_t nwords, uint32_t wlut_s, uint32_t sub_s, const DecArgs &a,
-                                            uint32_t *bad) {
-    while (w.b.addr < w.limit) walk_pair(w, wlut_s, sub_s, a, bad);
-    uint32_t end_rel = 32u * (nwords + 3u) - 8u * (w.b.addr - w.addr0);
-    while ((w.c & 127u) + kLutBits <= end_rel) {
-        const uint32_t e = lds_tab_u32(wlut_s + entry_offset(w.b, w.c));
-        if (e < 0x10000u) break;
-        w.c += e >> 16;
-        emit(w.r, e, e >> 27);
-    }
-    for (;;) {
-        if ((w.c & 127u) >= end_rel) break;
-        if (w.c & 32u) {
-            buf_shift(w.b);
-            w.c -= 32u;
-            end_rel -= 32u;
-        }
-        const uint32_t e = lds_tab_u32(wlut_s + entry_offset(w.b, w.c));
-        uint32_t sym = e & 0xffu, len = (e >> 23) & 15u;
-        if (e < 0x10000u) {
-            len = long_code_at(w.b, w.c & 31u, e, sub_s, a, &sym);
-            if (len == 0) {
-                *bad = 1u;
-                w.c += 1u;
-                continue;
-            }
-        }
-        w.c += len;
-        emit(w.r, sym, 8u);
-    }
-}
-// The write walk of one chunk: its two parts are decoded side by side (two independent dependency
-// chains per lane: the walk is a chain of dependent shifts and table loads, and a warp scheduler
-// with four warps cannot hide it otherwise).  chunk_s: shared address of the chunk's first word;
-// text_s: shared address of its first text byte; mid = entry of part two | symbols of part one << 16.
-__device__ __forceinline__ void lane_write(uint32_t chunk_s, uint32_t start, uint32_t mid, uint32_t text_s, uint32_t wlut_s,
-                                           uint32_t sub_s, const DecArgs &a, uint32_t *bad, OutAcc *ra, OutAcc *rb) {
-    WriteWalk wa, wb;
-    const uint32_t text_b = text_s + (mid >> 16);
-    walk_open(wa, chunk_s, kSplitWords, start, text_s);
-    walk_open(wb, chunk_s + 4 * kSplitWords, kLaneWords - kSplitWords, mid & 0xffffu, text_b);
-    while (wa.b.addr < wa.limit && wb.b.addr < wb.limit) {
-        const uint32_t ea1 = lds_tab_u32(wlut_s + entry_offset(wa.b, wa.c)), eb1 = lds_tab_u32(wlut_s + entry_offset(wb.b, wb.c));
-        wa.c += ea1 >> 16;
-        wb.c += eb1 >> 16;
-        const uint32_t ea = lds_tab_u32(wlut_s + entry_offset(wa.b, wa.c)), eb = lds_tab_u32(wlut_s + entry_offset(wb.b, wb.c));
-        wa.c += ea >> 16;
-        wb.c += eb >> 16;
-        emit_pair(wa.r, ea1, ea);
-        emit_pair(wb.r, eb1, eb);
-        if ((ea < eb ? ea : eb) < 0x10000u) {  // rare: one of them met a code of more than 12 bits
-            if (ea < 0x10000u) walk_long(wa, wlut_s, sub_s, a, bad);
-            if (eb < 0x10000u) walk_long(wb, wlut_s, sub_s, a, bad);
-        }
-        walk_refill(wa);
-        walk_refill(wb);
-    }
-    walk_finish(wa, kSplitWords, wlut_s, sub_s, a, bad);
-    walk_finish(wb, kLaneWords - kSplitWords, wlut_s, sub_s, a, bad);
-    *ra = wa.r;
-    *rb = wb.r;
-}
-// Write walk with every limit checked (a chunk at the ends of the stream): one symbol at a time.
-__device__ __noinline__ void lane_write_edge(uint32_t chunk_s, uint32_t start, const LaneGeom &l, uint32_t text_s, uint32_t wlut_s,
-                                             uint32_t sub_s, const DecArgs &a, uint32_t *bad, OutAcc *ra) {
-    OutAcc r;
-    r.lo = r.hi = 0;
-    r.A = text_s;
-    uint32_t pos = start;
-    while (pos < l.own_bits) {
-        uint32_t sym = 0;
-        const uint32_t len = edge_symbol(chunk_s, pos, 0, sub_s, a, &sym, true, wlut_s);
-        if (len == 0) {
-            *bad = 1u;
-            pos += 1;
-            continue;
-        }
-        if (pos + len > l.hard_bits) break;
-        pos += len;
-        emit(r, sym, 8u);
-    }
-    *ra = r;
-}
-
-// What the write walk of a region needs to know about it (loaded one region ahead).
-struct RegionMeta {
-    uint32_t cnt, start, prev_exit, mid;
-    unsigned long long o_w;
-    bool live;
-};
-__device__ __forceinline__ RegionMeta region_meta(const DecArgs &a, uint32_t r, uint32_t lane) {
-    RegionMeta m;
-    const uint32_t gc = r * 32 + lane;
-    m.live = gc < a.n_chunks;
-    m.cnt = m.live ? a.count[gc] : 0u;
-    m.start = m.live ? a.start_off[gc] : 0u;
-    m.mid = m.live ? a.mid[gc] : 0u;
-    m.prev_exit = (m.live && gc > 0) ? a.exit_off[gc - 1] : m.start;
-    m.o_w = a.block_prefix[r];
-    return m;
-}
-
-// Dynamic shared memory (smem_bytes, all an SM has): write table (16 KiB) | second-level tables (8 KiB) | per warp:
-// stream image (kImgBytes) + text stage (sized on the device from the largest region).
-// Persistent: one CTA per SM, every warp strides over the regions; the stream bytes and the
-// metadata of a warp's next region are requested before it walks the current one.
-__global__ void __launch_bounds__(512, 1) region_write_kernel(const DecArgs a, uint32_t n_regions, uint32_t smem_bytes) {
-    extern __shared__ __align__(16) uint8_t dyn[];
-    uint32_t *wlut_sh = reinterpret_cast<uint32_t *>(dyn);
-    uint16_t *sub_sh = reinterpret_cast<uint16_t *>(dyn + kLutSize * 4);
-    for (uint32_t i = threadIdx.x; i < (uint32_t)kLutSize; i += blockDim.x) {
-        const uint32_t e = a.wlut[i], add = e >> 16, len0 = (a.clut[i] >> 16) & 0xffu;
-        wlut_sh[i] = (add & kLutMarker) ? (uint32_t)(a.slots[i] == kNoSlot ? kNoSlot : (0x8000u | a.slots[i]))
-                                        : ((e & 0xffffu) | ((add & 0xffu) << 16) | (len0 << 23) | ((add >> 9) << 30));
-    }
-    for (uint32_t i = threadIdx.x; i < kSubBytes / 2; i += blockDim.x) sub_sh[i] = a.slots[kLutSize + i];
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // text stage of a warp: the largest region of this stream (found by the scan, read here so that the host
-    // does not have to look at it), 15 bytes of skew, whole vectors; as many warps as then fit the SM work
-    const uint32_t avail = smem_bytes - kTableBytes;
-    uint32_t stage_bytes = (*a.max_sum + 15u + 15u) & ~15u;
-    if (stage_bytes + kImgBytes > avail) stage_bytes = (avail - kImgBytes) & ~15u;  // regions that do not fit take the generic walker
-    uint32_t warps = avail / (stage_bytes + kImgBytes);
-    if (warps > (blockDim.x >> 5)) warps = blockDim.x >> 5;
-    if (warp >= warps) return;
-    const uint32_t stride = gridDim.x * warps;
-    uint32_t r = blockIdx.x * warps + warp;
-    if (r >= n_regions) return;
-    const uint32_t img_s = pinned(smem_addr(dyn) + kTableBytes + warp * (kImgBytes + stage_bytes));
-    const uint32_t stage_s = pinned(img_s + kImgBytes), wlut_s = pinned(smem_addr(wlut_sh)), sub_s = pinned(smem_addr(sub_sh));
-    uint32_t bad = 0;
-
-    RegionMeta m = region_meta(a, r, lane);
-    Region g = region_of(a, r);
-    RegionRegs q;
-    if (g.interior) region_load(a, g.begin_byte, lane, q);
-    for (;;) {
-        const uint32_t gc = r * 32 + lane;
-        const bool interior = g.interior;
-        if (interior) {
-            __syncwarp();  // the copy-out of the region before this one is done with the shared buffers
-            region_store(q, img_s, lane);
-        }
-        // request the next region
-        const uint32_t r_next = r + stride;
-        const RegionMeta m_cur = m;
-        if (r_next < n_regions) {
-            m = region_meta(a, r_next, lane);
-            g = region_of(a, r_next);
-            if (g.interior) region_load(a, g.begin_byte, lane, q);
-        }
-        // does every chunk start where its left neighbour ended?  (the fixpoint check rides along)
-        if (m_cur.live && gc > 0 && m_cur.prev_exit != m_cur.start) *a.changed = 1u;
-        const uint32_t cnt = m_cur.cnt;
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += up;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const unsigned long long o_w = m_cur.o_w;
-        if (total != 0 && o_w < a.max_symbols) {
-            const unsigned long long o = o_w + (incl - cnt);
-            const unsigned long long o_end = o_w + total < a.max_symbols ? o_w + total : a.max_symbols;
-            uint8_t *dst_w = a.out + o_w;
-            const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(dst_w) & 15u);  // text of other regions in the first vector
-            if (skew + total <= stage_bytes) {
-                if (!interior) {
-                    __syncwarp();
-                    region_stage_guarded(a, (a.grid_bit >> 3) + (uint64_t)r * kRegionBytes, img_s, lane);
-                }
-                __syncwarp();
-                const uint32_t text_s = stage_s + skew + (incl - cnt), chunk_s = img_s + 16 + lane * kLaneBytes;
-                OutAcc ra, rb;
-                ra.lo = ra.hi = rb.lo = rb.hi = 0;
-                ra.A = rb.A = text_s;
-                uint32_t text_b = text_s;  // where the second accumulator started
-                if (interior) {
-                    text_b = text_s + (m_cur.mid >> 16);
-                    lane_write(chunk_s, m_cur.start, m_cur.mid, text_s, wlut_s, sub_s, a, &bad, &ra, &rb);
-                } else if (m_cur.live && cnt) {
-                    const LaneGeom l = lane_geom(a, gc);
-                    if (l.fast && m_cur.start < 32u) {
-                        text_b = text_s + (m_cur.mid >> 16);
-                        lane_write(chunk_s, m_cur.start, m_cur.mid, text_s, wlut_s, sub_s, a, &bad, &ra, &rb);
-                    } else {
-                        lane_write_edge(chunk_s, m_cur.start, l, text_s, wlut_s, sub_s, a, &bad, &ra);
-                        rb.A = text_b = ra.A;
-                    }
-                }
-                // the bytes after the last whole word of either part leave once every lane has stored its whole words
-                __syncwarp();
-                lane_flush(ra, text_s);
-                lane_flush(rb, text_b);
-                __syncwarp();
-                // the stage is an image of the text from the 16-byte boundary below dst_w: whole vectors leave as such
-                uint8_t *base = dst_w - skew;
-                const uint32_t first = skew, last = skew + (uint32_t)(o_end - o_w);
-                const uint32_t n_vec = (last + 15u) >> 4;
-                for (uint32_t v = lane; v < n_vec; v += 32) {
-                    const uint32_t b0 = v * 16u;
-                    if (b0 >= first && b0 + 16u <= last) {
-                        uint4 w;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                     : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
-                                     : "r"(stage_s + b0));
-                        st_stream_v4(base + b0, w);
-                    } else {
-                        const uint32_t lo = b0 > first ? b0 : first, hi = b0 + 16u < last ? b0 + 16u : last;
-                        for (uint32_t k = lo; k < hi; ++k) base[k] = (uint8_t)lds_u8(stage_s + k);
-                    }
-                }
-            } else if (m_cur.live && cnt) {  // a region whose text does not fit the stage (more than 227 KiB of shared memory holds)
-                const Chunk k = chunk_of(a, gc);
-                uint32_t n = 0;
-                if (k.begin + m_cur.start < k.end) walk_generic<true>(a, k.begin + m_cur.start, k.end, a.end_bit, &n, o, &bad);
-            }
-        }
-        if (r_next >= n_regions) break;
-        r = r_next;
-    }
-    if (bad) atomicOr(a.error_flags, kErrInvalidCode);
-}
+#include "et_lanes.inc"
 
 uint64_t chunk_count(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t grid_bit = g.own_begin_bit / 256 * 256;
@@ -1340,7 +627,14 @@ cudaError_t unpack_init_device(int device, UnpackTuning *tune) {
     if ((err = cudaDeviceGetAttribute(&tune->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(region_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tune->max_smem)) != cudaSuccess)
         return err;
-    return cudaFuncSetAttribute(region_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmem);
+    if ((err = cudaFuncSetAttribute(region_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tune->max_smem)) != cudaSuccess)
+        return err;
+    // the lane-interleaved decoder's tables, built on the device for every stream (lane_tables_kernel)
+    return cudaMalloc(&tune->d_lane_tables, kCountTableBytes + kWriteTableBytes + kSingleTableBytes);
+}
+void unpack_free_device(UnpackTuning *tune) {
+    if (tune->d_lane_tables) cudaFree(tune->d_lane_tables);
+    tune->d_lane_tables = nullptr;
 }
 
 UnpackGeometry unpack_geometry(const void *d_body, size_t body_bytes) {
@@ -1411,20 +705,34 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
     cudaError_t err;
     const int max_smem = tune.max_smem, num_sms = tune.num_sms;
     const uint32_t *h_changed = reinterpret_cast<const uint32_t *>(h_hdr + 16);
-    const uint32_t sync_blocks = (n_regions + kSyncWarps - 1) / kSyncWarps;
-    const uint32_t resident = (uint32_t)num_sms * 2u;  // __launch_bounds__(.., 2)
-    const uint32_t sync_grid = sync_blocks < resident ? sync_blocks : resident;
+    // count walk: one CTA per SM, as many warps as images fit beside the tables
+    uint32_t sync_warps = ((uint32_t)max_smem - kSyncTableBytes) / kImgBytes;
+    if (sync_warps > kMaxLaneWarps) sync_warps = kMaxLaneWarps;
+    if (tune.sync_warps > 0 && (uint32_t)tune.sync_warps < sync_warps) sync_warps = (uint32_t)tune.sync_warps;
+    if (sync_warps > 4) sync_warps &= ~3u;  // the same number of warps on each of the SM's four schedulers: they share the regions evenly
+    const uint32_t sync_smem = kSyncTableBytes + sync_warps * kImgBytes;
+    const uint32_t sync_blocks = (n_regions + sync_warps - 1) / sync_warps;
+    const uint32_t sync_grid = sync_blocks < (uint32_t)num_sms ? sync_blocks : (uint32_t)num_sms;
+    DecArgs &am = const_cast<DecArgs &>(a);
+    unsigned long long *d_dbg = nullptr;
+    if (tune.debug) {
+        if (cudaMalloc(&d_dbg, 2 * 256 * 35 * 8) == cudaSuccess) cudaMemsetAsync(d_dbg, 0, 2 * 256 * 35 * 8, stream);
+    }
+    am.dbg = d_dbg;
+    lane_tables_kernel<<<(1u << 16) / 256, 256, 0, stream>>>(a.nodes, const_cast<uint16_t *>(a.t_count), const_cast<uint32_t *>(a.t_write),
+                                                            const_cast<uint8_t *>(a.t_single));
+    if (launches) *launches += 1;
     const uint32_t check_grid = (n_regions + 31u) / 32u;  // 8 warps x 4 regions per CTA
     // one repair round: list the regions with a wrong entry, walk those again from their neighbours' exits
     auto repair = [&](int round) -> cudaError_t {
         cudaError_t e = cudaMemsetAsync(a.work_count, 0, 4, stream);
         if (e != cudaSuccess) return e;
         region_check_kernel<<<check_grid, 256, 0, stream>>>(a, n_regions);
-        region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, round);
+        region_sync_kernel<<<sync_grid, sync_warps * 32, sync_smem, stream>>>(a, n_regions, round, sync_warps);
         if (launches) *launches += 2;
         return cudaSuccess;
     };
-    region_sync_kernel<<<sync_grid, kSyncWarps * 32, kSyncSmem, stream>>>(a, n_regions, 0);
+    region_sync_kernel<<<sync_grid, sync_warps * 32, sync_smem, stream>>>(a, n_regions, 0, sync_warps);
     if (launches) *launches += 1;
     if ((err = repair(1)) != cudaSuccess) return err;
     if ((err = cudaMemsetAsync(a.changed, 0, 8, stream)) != cudaSuccess) return err;  // changed and max_sum
@@ -1441,6 +749,30 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
         // one look at the scratch header: error flags, symbols found, "an entry was wrong", entry and exit of the shard
         if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
         if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
+        if (tune.debug && d_dbg) {
+            static unsigned long long h[2 * 256 * 35];
+            cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost);
+            for (int k = 0; k < 2; ++k) {
+                unsigned long long t0 = ~0ull, t1 = 0;
+                for (int i = 0; i < 256; ++i)
+                    if (h[(k * 256 + i) * 3 + 2]) {
+                        t0 = h[(k * 256 + i) * 3 + 1] < t0 ? h[(k * 256 + i) * 3 + 1] : t0;
+                        t1 = h[(k * 256 + i) * 3 + 2] > t1 ? h[(k * 256 + i) * 3 + 2] : t1;
+                    }
+                fprintf(stderr, "[lanes] %s kernel: %.1f us; per CTA (smid:start..end us):", k ? "write" : "sync", (t1 - t0) / 1e3);
+                for (int i = 0; i < 256; ++i)
+                    if (h[(k * 256 + i) * 3 + 2])
+                        fprintf(stderr, " %llu:%.0f..%.0f", h[(k * 256 + i) * 3], (h[(k * 256 + i) * 3 + 1] - t0) / 1e3, (h[(k * 256 + i) * 3 + 2] - t0) / 1e3);
+                fprintf(stderr, "\n");
+                int slow = 0;
+                for (int i = 0; i < 256; ++i)
+                    if (h[(k * 256 + i) * 3 + 2] > h[(k * 256 + slow) * 3 + 2]) slow = i;
+                fprintf(stderr, "[lanes] slowest block %d, its warps end at (us):", slow);
+                for (int w = 0; w < 32; ++w)
+                    if (h[2 * 256 * 3 + (k * 256 + slow) * 32 + w]) fprintf(stderr, " %d:%.0f", w, (h[2 * 256 * 3 + (k * 256 + slow) * 32 + w] - t0) / 1e3);
+                fprintf(stderr, "\n");
+            }
+        }
         if (tune.debug)
             fprintf(stderr, "[lanes] regions=%u chunks=%u max_sum=%u rounds=%u changed=%u\n", n_regions, a.n_chunks,
                     *reinterpret_cast<const uint32_t *>(h_hdr + 20), rounds, *h_changed);
@@ -1463,6 +795,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
         if ((err = cudaMemsetAsync(a.error_flags, 0, 4, stream)) != cudaSuccess) return err;  // raised by a wrong parse
     }
     if (rounds_out) *rounds_out = rounds;
+    if (d_dbg) cudaFree(d_dbg);
     return cudaGetLastError();
 }
 
@@ -1499,6 +832,9 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.wlut = d_wlut;
     a.nodes = d_nodes;
     a.slots = d_slots;
+    a.t_count = reinterpret_cast<const uint16_t *>(tune.d_lane_tables);
+    a.t_write = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(tune.d_lane_tables) + kCountTableBytes);
+    a.t_single = static_cast<const uint8_t *>(tune.d_lane_tables) + kCountTableBytes + kWriteTableBytes;
     // [pad(4) | error flags(4) | total(8) | changed(4) | pad(4) | entry/exit(8)] then the arrays
     a.error_flags = reinterpret_cast<uint32_t *>(p + 4);
     a.total = reinterpret_cast<unsigned long long *>(p + 8);
@@ -1515,6 +851,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.work_count = reinterpret_cast<uint32_t *>(p + 32);
     a.out = d_out;
     a.max_symbols = max_symbols;
+    a.dbg = nullptr;
 
     if (lanes) return launch_unpack_lanes(a, nb, p, h_hdr, stream, tune, launches, rounds_out);
 

@@ -116,6 +116,7 @@ ET_API uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx);
  * variables ET_LANE_MIN_BYTES and ET_DEBUG_LANES seed the first two when the context is created. */
 #define ET_TUNE_LANE_MIN_BYTES 1 /* bodies of at least this many bytes take the lane-interleaved decoder; -1 = default */
 #define ET_TUNE_DEBUG 2          /* non-zero: one line per decode on stderr */
+#define ET_TUNE_SYNC_WARPS 3     /* warps per CTA of the decoder's count walk; 0 = as many as fit */
 ET_API int et_ctx_set_tuning(et_ctx *ctx, int key, long long value);
 
 /* Pinned host memory for full-rate host<->device copies in et_encode/et_decode. */
