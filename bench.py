@@ -245,13 +245,22 @@ class OneGpu:
 class ManyGpus:
     """N>1: one stream sharded over the ranks (entreepy_b200.sharded on the shard entry points)."""
 
-    def __init__(self, codec, plan, dist, stream):
+    def __init__(self, codec, plan, dist, stream, py_exchange=False):
         import torch
 
         from entreepy_b200 import sharded
 
         self.codec, self.plan, self.dist = codec, plan, dist
-        self.coder = sharded.ShardedCodec(sharded.GpuBackend(codec, stream), plan, sharded.Comm(dist, torch.device("cuda")))
+        py_comm = sharded.Comm(dist, torch.device("cuda"))
+        if py_exchange:  # the exchanges in Python over torch.distributed (round 1's path, kept for comparison)
+            self.coder = sharded.ShardedCodec(sharded.GpuBackend(codec, stream), plan, py_comm)
+            self.path = "entreepy_b200.sharded.ShardedCodec (exchanges in Python over torch.distributed)"
+        else:  # the whole protocol behind the C ABI, its all-gathers on an NCCL communicator of the library's own
+            uid = [codec.comm_unique_id() if plan.rank == 0 else None]
+            dist.broadcast_object_list(uid, 0)
+            self.ncomm = codec.comm_nccl(uid[0], plan.rank, plan.world)
+            self.coder = sharded.NativeShardedCodec(codec, plan, self.ncomm, py_comm, stream)
+            self.path = "et_encode_sharded_dev + et_decode_sharded_dev (C ABI, ncclAllGather on the context's stream)"
         self.body = torch.empty(plan.n_local + 16384, dtype=torch.uint8, device="cuda")
         self.res = self.range = self.dec = None
 
@@ -411,7 +420,7 @@ def run_ours(args, rank, world):
     stream = torch.cuda.current_stream().cuda_stream
     thr = thresholds(kind) if kind != "file" else None
     inp = make_input(codec, args.workload, plan.lo, n, world)
-    arm = OneGpu(codec, n, stream) if world == 1 else ManyGpus(codec, plan, dist, stream)
+    arm = OneGpu(codec, n, stream) if world == 1 else ManyGpus(codec, plan, dist, stream, args.py_exchange)
 
     def barrier():
         if dist is not None:
@@ -537,6 +546,7 @@ def run_ours(args, rank, world):
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "bytes": n_total, "bytes_per_rank": n, "compressed_bytes_rank0": c_local,
                        "sharding": f"{world} contiguous byte ranges of one .et stream" if world > 1 else "none",
+                       "sharded_path": getattr(arm, "path", None),
                        "l2": "inputs larger than L2 (126 MB), no explicit flush"},
             "encode_gbs": n_total / 1e9 / (enc_ms / 1e3), "decode_gbs": n_total / 1e9 / (dec_ms / 1e3),
             "encode_ms": enc_ms, "decode_ms": dec_ms,
@@ -608,6 +618,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--py-exchange", action="store_true", help="N>1: the exchanges in Python over torch.distributed instead of inside the library")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (text-5M, adversarial, text-4G)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -20,8 +20,23 @@ SYMBOLS = [
     "et_ctx_kernel_launches", "et_ctx_last_stage_ms", "et_ctx_last_decode_rounds", "et_ctx_set_tuning", "et_alloc_pinned", "et_free_pinned", "et_build_codebook",
     "et_header_size", "et_write_header", "et_encode_bound", "et_parse_header", "et_histogram", "et_histogram_dev",
     "et_encode", "et_decode", "et_encode_dev", "et_decode_dev", "et_pack_shard_dev", "et_shard_bits",
-    "et_unpack_shard_dev", "et_synth_dev",
+    "et_unpack_shard_dev", "et_synth_dev", "et_comm_unique_id", "et_comm_create_nccl", "et_comm_create_callback", "et_comm_destroy",
+    "et_encode_sharded_dev", "et_decode_sharded_dev",
 ]
+COMM_ID_BYTES = 128
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
+class ShardEncoded(ctypes.Structure):
+    _fields_ = [
+        ("n_total", ctypes.c_uint64), ("total_bytes", ctypes.c_uint64), ("body_bytes", ctypes.c_uint64), ("bit_offset", ctypes.c_uint64),
+        ("first_byte", ctypes.c_uint64), ("local_bytes", ctypes.c_uint64), ("own_lo", ctypes.c_uint64), ("own_hi", ctypes.c_uint64),
+        ("header_len", ctypes.c_uint32), ("header", ctypes.c_uint8 * 4096),
+    ]
+
+
+class ShardDecoded(ctypes.Structure):
+    _fields_ = [("n_local", ctypes.c_uint64), ("offset", ctypes.c_uint64), ("body_len", ctypes.c_uint64), ("rounds", ctypes.c_uint32)]
 
 
 class Code(ctypes.Structure):
@@ -98,6 +113,12 @@ def load():
         "et_unpack_shard_dev": (i, [vp, vp, sz, sz, sz, ctypes.POINTER(Dictionary), ctypes.c_int64, vp, sz,
                                     ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(u64), vp]),
         "et_synth_dev": (i, [vp, vp, sz, u64, u64, vp, vp]),
+        "et_comm_unique_id": (i, [vp]),
+        "et_comm_create_nccl": (i, [vp, vp, i, i, ctypes.POINTER(vp)]),
+        "et_comm_create_callback": (i, [vp, i, i, ALLGATHER_FN, vp, ctypes.POINTER(vp)]),
+        "et_comm_destroy": (None, [vp]),
+        "et_encode_sharded_dev": (i, [vp, vp, vp, sz, vp, sz, ctypes.POINTER(ShardEncoded), u32, vp]),
+        "et_decode_sharded_dev": (i, [vp, vp, vp, sz, vp, sz, sz, sz, i, vp, sz, ctypes.POINTER(ShardDecoded), u32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -240,6 +240,58 @@ class Codec:
                                                   stream))
         return n.value, ent.value, ext.value
 
+    # ---- the sharded path with its exchanges inside the library (et_encode_sharded_dev / et_decode_sharded_dev)
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes made by rank 0 (ncclGetUniqueId) for et_comm_create_nccl on every rank."""
+        buf = (ctypes.c_uint8 * _abi.COMM_ID_BYTES)()
+        rc = _abi.load().et_comm_unique_id(buf)
+        if rc:
+            raise EntreepyError(rc, "libnccl.so.2 is not available")
+        return bytes(buf)
+
+    def comm_nccl(self, unique_id, rank, world):
+        """et_comm over NCCL (all ranks call this together: ncclCommInitRank)."""
+        comm = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * _abi.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self._lib.et_comm_create_nccl(self._ctx, buf, rank, world, ctypes.byref(comm)))
+        return comm
+
+    def comm_callback(self, rank, world, allgather):
+        """et_comm over a host transport: allgather(send: bytes) -> bytes of every rank's block in rank order."""
+        def tramp(_user, send, recv, nbytes):
+            try:
+                got = allgather(ctypes.string_at(send, nbytes))
+                assert len(got) == nbytes * world
+                ctypes.memmove(recv, got, len(got))
+                return 0
+            except Exception:  # noqa: BLE001 - reported as a failed exchange
+                return 1
+
+        fn = _abi.ALLGATHER_FN(tramp)
+        comm = ctypes.c_void_p()
+        self._check(self._lib.et_comm_create_callback(self._ctx, rank, world, fn, None, ctypes.byref(comm)))
+        self._keep = getattr(self, "_keep", []) + [fn]  # the C side holds the pointer
+        return comm
+
+    def comm_destroy(self, comm):
+        self._lib.et_comm_destroy(comm)
+
+    def encode_sharded_dev(self, comm, d_in, n_local, d_out, cap, flags=0, stream=None):
+        """One rank of the sharded encoder -> _abi.ShardEncoded."""
+        res = _abi.ShardEncoded()
+        self._check(self._lib.et_encode_sharded_dev(self._ctx, comm, d_in, n_local, d_out, cap, ctypes.byref(res), flags, stream))
+        return res
+
+    def decode_sharded_dev(self, comm, header_after_magic, d_range, range_bytes, own_begin, own_end, starts_body, d_out, cap,
+                           flags=0, stream=None):
+        """One rank of the sharded decoder -> _abi.ShardDecoded."""
+        h = _u8(header_after_magic)
+        res = _abi.ShardDecoded()
+        self._check(self._lib.et_decode_sharded_dev(self._ctx, comm, h.ctypes.data, h.size, d_range, range_bytes, own_begin, own_end,
+                                                    1 if starts_body else 0, d_out, cap, ctypes.byref(res), flags, stream))
+        return res
+
     def synth_dev(self, d_out, n, seed, first_index, thresholds, stream=None):
         t = np.ascontiguousarray(thresholds, dtype=np.uint32)
         assert t.size == 256

@@ -17,6 +17,10 @@
 
 using namespace et;
 
+struct ncclUniqueIdBytes {  // layout of ncclUniqueId (nccl.h): passed by value to ncclCommInitRank
+    char b[ET_COMM_ID_BYTES];
+};
+
 struct et_ctx {
     int device = 0;
     int num_sms = 0;
@@ -756,3 +760,5 @@ extern "C" int et_synth_dev(et_ctx *ctx, void *d_out, size_t n, uint64_t seed, u
     ET_CUDA(ctx, cudaStreamSynchronize(s));
     return ET_OK;
 }
+
+#include "et_shard.inc"

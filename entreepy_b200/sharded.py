@@ -362,3 +362,33 @@ class ShardedCodec:
         offset = sum(info[r][0] for r in range(p.rank))
         valid = max(min(info[p.rank][0], int(dictionary.body_len) - offset), 0)
         return DecodeResult(n_local=valid, offset=offset, rounds=rounds)
+
+
+class NativeShardedCodec(ShardedCodec):
+    """The same protocol with the exchanges INSIDE the library: et_encode_sharded_dev / et_decode_sharded_dev run the
+    kernels, the all-gathers (NCCL on the context's stream, or a host callback) and the host steps between them, so a
+    step costs one call per direction and no Python between kernel and collective.  `comm` is an et_comm made by
+    Codec.comm_nccl / Codec.comm_callback; `py_comm` (a Comm) is only used by scatter_body, the file reader's job."""
+
+    def __init__(self, codec, plan, comm, py_comm, stream=None):
+        super().__init__(GpuBackend(codec, stream), plan, py_comm)
+        self.codec, self.ncomm, self.stream = codec, comm, stream
+
+    def encode(self, t_in, t_out):
+        p = self.plan
+        r = self.codec.encode_sharded_dev(self.ncomm, t_in.data_ptr(), p.n_local, t_out.data_ptr(), t_out.numel(), 0, self.stream)
+        self.backend.hist_ms = self.codec.last_stage_ms()[0]
+        res = EncodeResult(total_bytes=int(r.total_bytes), header=bytes(r.header[: r.header_len]), bit_offsets=[0, int(r.body_bytes) * 8],
+                           first_byte=int(r.first_byte), local_bytes=int(r.local_bytes), own_lo=int(r.own_lo), own_hi=int(r.own_hi))
+        res.bit_offset = int(r.bit_offset)
+        res.n_total = int(r.n_total)
+        return res
+
+    def decode(self, header, body_bytes, t_range, t_out):
+        p = self.plan
+        cuts, ranges = self.decode_ranges(body_bytes)
+        s, t = ranges[p.rank]
+        own_begin, own_end = cuts[p.rank] - s, cuts[p.rank + 1] - s
+        r = self.codec.decode_sharded_dev(self.ncomm, header, t_range.data_ptr(), t - s, own_begin, own_end, cuts[p.rank] == 0,
+                                          t_out.data_ptr(), t_out.numel(), 0, self.stream)
+        return DecodeResult(n_local=int(r.n_local), offset=int(r.offset), rounds=int(r.rounds))

@@ -185,6 +185,51 @@ ET_API int et_unpack_shard_dev(et_ctx *ctx, const void *d_range, size_t range_by
                         size_t own_end_byte, const et_dictionary *dict, int64_t head_bit, void *d_out, size_t cap,
                         uint64_t *n_symbols, uint64_t *entry_bit, uint64_t *exit_bit, void *stream);
 
+/* ------------------------------------------------------------------ sharded path, the whole protocol of one rank */
+/* The exchanges of the sharded path are all-gathers of a few hundred bytes per rank.  An et_comm carries them:
+ * over NCCL (libnccl.so.2 is opened at run time; rank 0 makes an id with et_comm_unique_id and hands it to the
+ * others by whatever means the host program has), or through a host callback. */
+#define ET_COMM_ID_BYTES 128 /* = NCCL_UNIQUE_ID_BYTES */
+typedef struct et_comm et_comm;
+/* Gathers `bytes` from every rank: send -> recv[rank * bytes] on all ranks (host memory).  0 = ok. */
+typedef int (*et_allgather_fn)(void *user, const void *send, void *recv, size_t bytes);
+ET_API int et_comm_unique_id(uint8_t out[ET_COMM_ID_BYTES]);
+ET_API int et_comm_create_nccl(et_ctx *ctx, const uint8_t id[ET_COMM_ID_BYTES], int rank, int world, et_comm **out);
+ET_API int et_comm_create_callback(et_ctx *ctx, int rank, int world, et_allgather_fn fn, void *user, et_comm **out);
+ET_API void et_comm_destroy(et_comm *comm);
+
+typedef struct et_shard_encoded {
+    uint64_t n_total;      /* bytes of the whole text (sum of the ranks' n_local) */
+    uint64_t total_bytes;  /* size of the whole .et file */
+    uint64_t body_bytes;
+    uint64_t bit_offset;   /* bit of the body at which this rank's first code sits (the cross-GPU exclusive scan) */
+    uint64_t first_byte;   /* body byte index of d_out[0] */
+    uint64_t local_bytes;  /* bytes this rank wrote: d_out[0 .. local_bytes) */
+    uint64_t own_lo, own_hi; /* body bytes [own_lo, own_hi) are final in this rank's buffer: the .et file is the header
+                                followed by every rank's d_out[own_lo - first_byte .. own_hi - first_byte) in rank order */
+    uint32_t header_len;
+    uint8_t header[4096];  /* magic .. dictionary pad: the same on every rank */
+} et_shard_encoded;
+/* encode() of SURVEY §8e for one rank: histogram of the rank's slice, ONE all-gather (histograms, text heads,
+ * lengths), codebook + header + bit-offset scan on every rank alike, pack at the final bit position, seam byte.
+ * d_out needs ceil((7 + bits of the slice) / 8) bytes; n_local + 16 is what the 7200+n bound guarantees. */
+ET_API int et_encode_sharded_dev(et_ctx *ctx, et_comm *comm, const void *d_in, size_t n_local, void *d_out, size_t cap,
+                          et_shard_encoded *res, uint32_t flags, void *stream);
+
+typedef struct et_shard_decoded {
+    uint64_t n_local;  /* valid symbols in d_out */
+    uint64_t offset;   /* position of the first of them in the text */
+    uint64_t body_len; /* symbols of the whole stream (the header's length field) */
+    uint32_t rounds;   /* 1 = every rank's guessed entry was right */
+} et_shard_decoded;
+/* decode() of SURVEY §8e for one rank.  header_after_magic: the .et bytes after the magic up to the body (every rank
+ * has them); d_range / own_*_byte as for et_unpack_shard_dev; starts_body: this rank's share begins with the body
+ * (its first codeword is known).  Ranks whose share is empty pass own_begin_byte == own_end_byte.  One all-gather
+ * per round; a rank whose guessed entry was not its left neighbour's exit decodes again from there. */
+ET_API int et_decode_sharded_dev(et_ctx *ctx, et_comm *comm, const uint8_t *header_after_magic, size_t header_len, const void *d_range,
+                          size_t range_bytes, size_t own_begin_byte, size_t own_end_byte, int starts_body, void *d_out, size_t cap,
+                          et_shard_decoded *res, uint32_t flags, void *stream);
+
 /* ------------------------------------------------------------------ synthetic inputs (bench/test utility) */
 /* out[i] = smallest s with thresholds[s] > (splitmix64(seed + first_index + i) >> 32);
  * same definition as entreepy_b200/synth.py on the CPU. */

@@ -229,7 +229,7 @@ class ThreadComm:
         return torch.cat(mine) if mine else torch.empty(0, dtype=torch.uint8, device=send.device)
 
 
-def _run_ranks(world, data, results):
+def _run_ranks(world, data, results, native=False):
     import torch
 
     shared = {"slots": [None] * world, "barrier": threading.Barrier(world)}
@@ -240,7 +240,12 @@ def _run_ranks(world, data, results):
             torch.cuda.set_device(0)
             with et.Codec(0) as codec:
                 plan = sharded.ShardPlan(data.size, world, rank)
-                coder = sharded.ShardedCodec(sharded.GpuBackend(codec), plan, ThreadComm(world, rank, shared))
+                tcomm = ThreadComm(world, rank, shared)
+                if native:  # the protocol inside the library; its all-gathers come back to this process through a callback
+                    ncomm = codec.comm_callback(rank, world, lambda send: b"".join(tcomm._exchange(send)))
+                    coder = sharded.NativeShardedCodec(codec, plan, ncomm, tcomm)
+                else:
+                    coder = sharded.ShardedCodec(sharded.GpuBackend(codec), plan, tcomm)
                 t_in = torch.from_numpy(data[plan.lo : plan.hi].copy()).cuda()
                 t_body = torch.zeros(plan.n_local * 4 + 4096, dtype=torch.uint8, device="cuda")
                 torch.cuda.synchronize()
@@ -253,6 +258,8 @@ def _run_ranks(world, data, results):
                 torch.cuda.synchronize()
                 dres = coder.decode(res.header[4:], res.body_bytes, t_range, t_out)
                 results[rank] = (res.header, mine, res.total_bytes, dres.offset, t_out[: dres.n_local].cpu().numpy().tobytes(), dres.rounds)
+                if native:
+                    codec.comm_destroy(ncomm)
         except BaseException as exc:  # noqa: BLE001 - reported by the test thread
             errors.append((rank, exc))
             shared["barrier"].abort()
@@ -266,9 +273,9 @@ def _run_ranks(world, data, results):
         raise errors[0][1]
 
 
-def _check_protocol(world, name, data):
+def _check_protocol(world, name, data, native=False):
     results = [None] * world
-    _run_ranks(world, data, results)
+    _run_ranks(world, data, results, native)
     want = _oracle_et(data)
     header = results[0][0]
     assert header + b"".join(r[1] for r in results) == want, f"{name}: sharded .et differs from the oracle's (world {world})"
@@ -297,3 +304,20 @@ def test_sharded_protocol_on_real_kernels(world):
             _check_protocol(world, name, case)
     if world == 3:
         _check_protocol(world, "fib32", _fib32())
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_protocol_inside_the_library(world):
+    """et_encode_sharded_dev / et_decode_sharded_dev (exchanges through an et_comm) against the oracle."""
+    rng = np.random.default_rng(200 + world)
+    assert _check_protocol(world, "text", _text(2_000_003, seed=10 + world), native=True) == 1
+    rounds = _check_protocol(world, "uniform255", rng.integers(1, 256, 700_001, dtype=np.uint8), native=True)
+    assert world == 2 or rounds >= 2
+    _check_protocol(world, "all256", np.concatenate([rng.integers(0, 256, 90_000, dtype=np.uint8), np.full(3000, 255, np.uint8),
+                                                     rng.integers(0, 256, 50_000, dtype=np.uint8)]), native=True)
+    _check_protocol(world, "tiny", _text(50 + world), native=True)
+    for name, case in make_cases().items():
+        if np.unique(case).size >= 2 and case.size >= 16 * world:
+            _check_protocol(world, name, case, native=True)
+    if world == 3:
+        _check_protocol(world, "fib32", _fib32(), native=True)
