@@ -350,19 +350,28 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t w = rw[q];
-#pragma unroll
-                        for (int p = 0; p < 2; ++p) {
-                            const int sa = 16 * p, sb = sa + 8;
-                            const uint32_t oa = sa == 0 ? ((w << 7) & 0x7f80u) : ((w >> (sa - 7)) & 0x7f80u);
-                            const uint32_t ob = (w >> (sb - 7)) & 0x7f80u;
-                            const uint2 ea = *reinterpret_cast<const uint2 *>(table_lane + oa);
-                            const uint2 eb = *reinterpret_cast<const uint2 *>(table_lane + ob);
-                            const uint32_t len = ea.y + eb.y;
-                            if (len <= 32u) {
-                                push_acc(acc, __funnelshift_lc(0u, ea.x, eb.y) | eb.x, len);
-                            } else {  // rare: a pair of more than 32 bits goes in as two codes
-                                push_acc(acc, ea.x, ea.y);
-                                push_acc(acc, eb.x, eb.y);
+                        // the four symbols of a word: their codes are merged in registers and go into the accumulator
+                        // as ONE piece when they fit 32 bits together (text: ~19 bits), else as two pairs, else one by one
+                        const uint2 e0 = *reinterpret_cast<const uint2 *>(table_lane + ((w << 7) & 0x7f80u));
+                        const uint2 e1 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 1) & 0x7f80u));
+                        const uint2 e2 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 9) & 0x7f80u));
+                        const uint2 e3 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 17) & 0x7f80u));
+                        const uint32_t l01 = e0.y + e1.y, l23 = e2.y + e3.y, len = l01 + l23;
+                        if (len <= 32u) {
+                            const uint32_t c01 = __funnelshift_lc(0u, e0.x, e1.y) | e1.x, c23 = __funnelshift_lc(0u, e2.x, e3.y) | e3.x;
+                            push_acc(acc, __funnelshift_lc(0u, c01, l23) | c23, len);
+                        } else {
+                            if (l01 <= 32u) {
+                                push_acc(acc, __funnelshift_lc(0u, e0.x, e1.y) | e1.x, l01);
+                            } else {
+                                push_acc(acc, e0.x, e0.y);
+                                push_acc(acc, e1.x, e1.y);
+                            }
+                            if (l23 <= 32u) {
+                                push_acc(acc, __funnelshift_lc(0u, e2.x, e3.y) | e3.x, l23);
+                            } else {
+                                push_acc(acc, e2.x, e2.y);
+                                push_acc(acc, e3.x, e3.y);
                             }
                         }
                     }

@@ -8,12 +8,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "c16w14": ["ET_COUNT_BITS=16", "ET_WRITE_BITS=14"],
     "c15w14": ["ET_COUNT_BITS=15", "ET_WRITE_BITS=14"],
-    "c14w14": ["ET_COUNT_BITS=14", "ET_WRITE_BITS=14"],
-    "c16w13": ["ET_COUNT_BITS=16", "ET_WRITE_BITS=13"],
-    "c15w13s17": ["ET_COUNT_BITS=15", "ET_WRITE_BITS=13", "ET_SPLIT_WORDS=17"],
-    "c15w15": ["ET_COUNT_BITS=15", "ET_WRITE_BITS=15"],
+    "c15w14alu": ["ET_COUNT_BITS=15", "ET_WRITE_BITS=14", "ET_FMA_SHIFTS=0"],
+    "c15w13": ["ET_COUNT_BITS=15", "ET_WRITE_BITS=13"],
+    "c16w14": ["ET_COUNT_BITS=16", "ET_WRITE_BITS=14"],
 }
 if sys.argv[1] == "build":
     from entreepy_b200 import build
