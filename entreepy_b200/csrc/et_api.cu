@@ -195,7 +195,7 @@ int pack_dev(et_ctx *ctx, const void *d_in, size_t n, const et_codebook &cb, uin
     const PackScratch ps = pack_scratch_carve(ctx->d_scratch, g.num_tiles);
     int launches = 0;
     ET_CUDA(ctx, launch_pack(g, ctx->d_small + kOffPackTables, wide, cb.max_length, d_body, bit_phase, ps, ctx->d_scratch, sb,
-                             ctx->num_sms, s, &launches));
+                             ctx->num_sms, s, &launches, ctx->tune.pack_single_pass != 0));
     ctx->launches += (uint64_t)launches;
     return ET_OK;
 }
@@ -313,6 +313,7 @@ extern "C" int et_ctx_set_tuning(et_ctx *ctx, int key, long long value) {
         case ET_TUNE_LANE_MIN_BYTES: ctx->tune.lane_min_bytes = value; return ET_OK;
         case ET_TUNE_DEBUG: ctx->tune.debug = value != 0; return ET_OK;
         case ET_TUNE_SYNC_WARPS: ctx->tune.sync_warps = (int)value; return ET_OK;
+        case ET_TUNE_PACK_SINGLE_PASS: ctx->tune.pack_single_pass = value != 0; return ET_OK;
     }
     return fail(ctx, ET_ERR_INVALID_ARG, "unknown tuning key %d", key);
 }

@@ -43,7 +43,7 @@ PackScratch pack_scratch_carve(void *base, uint32_t num_tiles);
 // max_len: longest code (sizes the bit image of a warp on the narrow path).
 cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint32_t max_len, uint8_t *d_out, uint32_t bit_phase,
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
-                        cudaStream_t stream, int *launches);
+                        cudaStream_t stream, int *launches, bool single_pass = false);
 
 // ---------------------------------------------------------------- K3-K5 (chunked self-synchronising decoder)
 constexpr int kSubseqBits = 128;    // a piece: the unit the stream is read in (one 16-byte load)
@@ -77,6 +77,7 @@ struct UnpackTuning {
     int max_smem = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int num_sms = 0;
     int sync_warps = 0;             // > 0: warps per CTA of the count walk (default: as many as fit)
+    int pack_single_pass = 0;       // non-zero: the encoder packs in ONE pass with a decoupled look-back (measured slower, see et_pack.cu)
     void *d_lane_tables = nullptr;  // device-built tables of the lane-interleaved decoder
 };
 cudaError_t unpack_init_device(int device, UnpackTuning *tune);

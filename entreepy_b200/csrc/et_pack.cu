@@ -72,6 +72,7 @@ struct PackArgs {
     uint16_t *run_bits;                // [32 * regions] lane-run pack: bits of every run of 64 symbols
     uint32_t n_regions;                // lane-run pack: regions of 2048 symbols (one warp each)
     uint32_t image_words;              // lane-run pack: words of a warp's bit image (guard included)
+    unsigned long long *tile_desc;     // single-pass pack: look-back descriptors, one per tile of `warps` regions
 };
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, uint32_t lane) {
@@ -295,6 +296,131 @@ __device__ __forceinline__ void load_run(const PackArgs &a, uint32_t r, uint32_t
     }
 }
 
+// The 64 symbols of a lane's run through the accumulator (their codes from the lane's column of the shared table).
+__device__ __forceinline__ void pack_run_symbols(BitAcc &acc, const uint4 (&raw)[4], unsigned long long valid, bool interior,
+                                                 const uint8_t *table_lane) {
+    if (interior) {
+        uint4 v0 = raw[0], v1 = raw[1], v2 = raw[2], v3 = raw[3];
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {  // one 16-byte vector per trip: the body must stay inside the instruction cache
+            const uint32_t rw[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t w = rw[q];
+                // the four symbols of a word: their codes are merged in registers and go into the accumulator
+                // as ONE piece when they fit 32 bits together (text: ~19 bits), else as two pairs, else one by one
+                const uint2 e0 = *reinterpret_cast<const uint2 *>(table_lane + ((w << 7) & 0x7f80u));
+                const uint2 e1 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 1) & 0x7f80u));
+                const uint2 e2 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 9) & 0x7f80u));
+                const uint2 e3 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 17) & 0x7f80u));
+                const uint32_t l01 = e0.y + e1.y, l23 = e2.y + e3.y, len = l01 + l23;
+                if (len <= 32u) {
+                    const uint32_t c01 = __funnelshift_lc(0u, e0.x, e1.y) | e1.x, c23 = __funnelshift_lc(0u, e2.x, e3.y) | e3.x;
+                    push_acc(acc, __funnelshift_lc(0u, c01, l23) | c23, len);
+                } else {
+                    if (l01 <= 32u) {
+                        push_acc(acc, __funnelshift_lc(0u, e0.x, e1.y) | e1.x, l01);
+                    } else {
+                        push_acc(acc, e0.x, e0.y);
+                        push_acc(acc, e1.x, e1.y);
+                    }
+                    if (l23 <= 32u) {
+                        push_acc(acc, __funnelshift_lc(0u, e2.x, e3.y) | e3.x, l23);
+                    } else {
+                        push_acc(acc, e2.x, e2.y);
+                        push_acc(acc, e3.x, e3.y);
+                    }
+                }
+            }
+            v0 = v1;
+            v1 = v2;
+            v2 = v3;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {  // ragged ends of the input: one symbol at a time, only those that exist
+            const uint4 v = raw[q >> 2];
+            uint32_t w = (q & 3) == 0 ? v.x : (q & 3) == 1 ? v.y : (q & 3) == 2 ? v.z : v.w;
+            uint32_t ok = (uint32_t)(valid >> (4 * q)) & 15u;
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k, w >>= 8, ok >>= 1) {
+                const uint2 e = *reinterpret_cast<const uint2 *>(table_lane + (w & 0xffu) * (kTableLanes * 8));
+                if (ok & 1u) push_acc(acc, e.x, e.y);
+            }
+        }
+    }
+}
+
+// The finished bit image of region r (region bit b in word kStageGuard + (b >> 5), MSB first) goes to its place in the
+// output: shifted to the region's final bit position, swapped to stream order, stored as aligned 16-byte vectors; the
+// (at most two) bytes it shares with its neighbours go to the seam arrays.
+__device__ __forceinline__ void region_copy_out(const PackArgs &a, uint32_t r, const uint32_t *stage, uint8_t *edge,
+                                                unsigned long long bit_begin, uint32_t region_bits, uint32_t lane) {
+    const unsigned long long bit_end = bit_begin + region_bits;
+    uint8_t *first_byte = a.out + (bit_begin >> 3);              // byte holding the region's first bit
+    const uint32_t align = (uint32_t)(reinterpret_cast<uintptr_t>(first_byte) & 15u);
+    uint8_t *gbase = first_byte - align;                         // frame byte k <-> gbase[k]
+    const uint32_t shift = align * 8 + (uint32_t)(bit_begin & 7);  // frame bit of region bit 0 (< 128)
+    const uint32_t used_bits = shift + region_bits;
+    const uint32_t n_chunks = (used_bits + 127u) >> 7;
+    {
+        const unsigned long long byte0 = bit_begin >> 3;
+        const unsigned long long full_lo = (bit_begin + 7) >> 3, full_hi = bit_end >> 3;  // owned bytes [lo,hi)
+        const uint32_t s_lo = (uint32_t)(full_lo - byte0) + align;                       // frame coordinates
+        const uint32_t s_hi = full_hi >= full_lo ? (uint32_t)(full_hi - byte0) + align : s_lo;
+        const bool has_head = (bit_begin & 7) != 0;
+        const bool has_tail = (bit_end & 7) != 0 && full_hi >= full_lo;
+        const uint32_t s_head = align;
+        const uint32_t s_tail = (uint32_t)(full_hi - byte0) + align;  // only meaningful when has_tail
+        if (lane == 0) {
+            if (!has_head) a.seam_head[r] = 0;
+            if (!has_tail) a.seam_tail[r] = 0;
+        }
+        // frame word f holds region bits [32f - shift, 32f - shift + 32): image word f - ws shifted right by bs
+        // bits, its top bits coming from the word before.  Two aligned 16-byte shared loads per chunk (the four
+        // image words of the chunk and the four before them: conflict-free), then a warp-uniform choice of which
+        // of the eight words feed which frame word.
+        const uint32_t bs = shift & 31u, ws = shift >> 5;
+        for (uint32_t c = lane; c < n_chunks; c += 32) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(stage + kStageGuard) + c;
+            const uint4 p = src[-1], q = src[0];
+            uint32_t f0, f1, f2, f3;
+            switch (ws) {
+                case 0:
+                    f0 = __funnelshift_r(q.x, p.w, bs); f1 = __funnelshift_r(q.y, q.x, bs);
+                    f2 = __funnelshift_r(q.z, q.y, bs); f3 = __funnelshift_r(q.w, q.z, bs);
+                    break;
+                case 1:
+                    f0 = __funnelshift_r(p.w, p.z, bs); f1 = __funnelshift_r(q.x, p.w, bs);
+                    f2 = __funnelshift_r(q.y, q.x, bs); f3 = __funnelshift_r(q.z, q.y, bs);
+                    break;
+                case 2:
+                    f0 = __funnelshift_r(p.z, p.y, bs); f1 = __funnelshift_r(p.w, p.z, bs);
+                    f2 = __funnelshift_r(q.x, p.w, bs); f3 = __funnelshift_r(q.y, q.x, bs);
+                    break;
+                default:
+                    f0 = __funnelshift_r(p.y, p.x, bs); f1 = __funnelshift_r(p.z, p.y, bs);
+                    f2 = __funnelshift_r(p.w, p.z, bs); f3 = __funnelshift_r(q.x, p.w, bs);
+                    break;
+            }
+            const uint4 v = make_uint4(bswap32(f0), bswap32(f1), bswap32(f2), bswap32(f3));
+            const uint32_t k0 = c * 16;
+            if (k0 >= s_lo && k0 + 16 <= s_hi) {
+                st_stream_v4(gbase + k0, v);
+            } else {
+                // a block at the ragged start or end of the region: bytewise, through a small buffer
+                uint4 *tmp = reinterpret_cast<uint4 *>(edge + (c == 0 ? 0 : 16));
+                *tmp = v;
+                const uint8_t *tb = reinterpret_cast<const uint8_t *>(tmp);
+                const uint32_t lo_k = max(k0, s_lo), hi_k = min(k0 + 16u, s_hi);
+                for (uint32_t kk = lo_k; kk < hi_k; ++kk) gbase[kk] = tb[kk - k0];
+                if (has_head && s_head >= k0 && s_head < k0 + 16u) a.seam_head[r] = tb[s_head - k0];
+                if (has_tail && s_tail >= k0 && s_tail < k0 + 16u) a.seam_tail[r] = tb[s_tail - k0];
+            }
+        }
+    }
+}
+
 // Pass B.  Dynamic shared memory: table (32 KiB, 16-lane replicated) | per warp: bit image | per warp: 32 edge bytes.
 __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const PackArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -342,125 +468,146 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
             BitAcc acc;
             acc.hi = acc.lo = 0;
             acc.pos = (uint32_t)__cvta_generic_to_shared(stage + kStageGuard) * 8u + my_off;
-            if (interior) {
-                uint4 v0 = raw[0], v1 = raw[1], v2 = raw[2], v3 = raw[3];
-#pragma unroll 1
-                for (int it = 0; it < 4; ++it) {  // one 16-byte vector per trip: the body must stay inside the instruction cache
-                    const uint32_t rw[4] = {v0.x, v0.y, v0.z, v0.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t w = rw[q];
-                        // the four symbols of a word: their codes are merged in registers and go into the accumulator
-                        // as ONE piece when they fit 32 bits together (text: ~19 bits), else as two pairs, else one by one
-                        const uint2 e0 = *reinterpret_cast<const uint2 *>(table_lane + ((w << 7) & 0x7f80u));
-                        const uint2 e1 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 1) & 0x7f80u));
-                        const uint2 e2 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 9) & 0x7f80u));
-                        const uint2 e3 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 17) & 0x7f80u));
-                        const uint32_t l01 = e0.y + e1.y, l23 = e2.y + e3.y, len = l01 + l23;
-                        if (len <= 32u) {
-                            const uint32_t c01 = __funnelshift_lc(0u, e0.x, e1.y) | e1.x, c23 = __funnelshift_lc(0u, e2.x, e3.y) | e3.x;
-                            push_acc(acc, __funnelshift_lc(0u, c01, l23) | c23, len);
-                        } else {
-                            if (l01 <= 32u) {
-                                push_acc(acc, __funnelshift_lc(0u, e0.x, e1.y) | e1.x, l01);
-                            } else {
-                                push_acc(acc, e0.x, e0.y);
-                                push_acc(acc, e1.x, e1.y);
-                            }
-                            if (l23 <= 32u) {
-                                push_acc(acc, __funnelshift_lc(0u, e2.x, e3.y) | e3.x, l23);
-                            } else {
-                                push_acc(acc, e2.x, e2.y);
-                                push_acc(acc, e3.x, e3.y);
-                            }
-                        }
-                    }
-                    v0 = v1;
-                    v1 = v2;
-                    v2 = v3;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {  // ragged ends of the input: one symbol at a time, only those that exist
-                    const uint4 v = raw[q >> 2];
-                    uint32_t w = (q & 3) == 0 ? v.x : (q & 3) == 1 ? v.y : (q & 3) == 2 ? v.z : v.w;
-                    uint32_t ok = (uint32_t)(valid >> (4 * q)) & 15u;
-#pragma unroll 1
-                    for (int k = 0; k < 4; ++k, w >>= 8, ok >>= 1) {
-                        const uint2 e = *reinterpret_cast<const uint2 *>(table_lane + (w & 0xffu) * (kTableLanes * 8));
-                        if (ok & 1u) push_acc(acc, e.x, e.y);
-                    }
-                }
-            }
+            pack_run_symbols(acc, raw, valid, interior, table_lane);
             __syncwarp();  // every whole word is in place
             if (acc.pos & 31u) atomicOr(stage + kStageGuard + ((my_off + my_bits) >> 5), acc.lo << (32u - (acc.pos & 31u)));
         }
         __syncwarp();  // image complete
-        uint8_t *first_byte = a.out + (bit_begin >> 3);              // byte holding the region's first bit
-        const uint32_t align = (uint32_t)(reinterpret_cast<uintptr_t>(first_byte) & 15u);
-        uint8_t *gbase = first_byte - align;                         // frame byte k <-> gbase[k]
-        const uint32_t shift = align * 8 + (uint32_t)(bit_begin & 7);  // frame bit of region bit 0 (< 128)
-        const uint32_t used_bits = shift + region_bits;
-        const uint32_t n_chunks = (used_bits + 127u) >> 7;
-        {
-            const unsigned long long byte0 = bit_begin >> 3;
-            const unsigned long long full_lo = (bit_begin + 7) >> 3, full_hi = bit_end >> 3;  // owned bytes [lo,hi)
-            const uint32_t s_lo = (uint32_t)(full_lo - byte0) + align;                       // frame coordinates
-            const uint32_t s_hi = full_hi >= full_lo ? (uint32_t)(full_hi - byte0) + align : s_lo;
-            const bool has_head = (bit_begin & 7) != 0;
-            const bool has_tail = (bit_end & 7) != 0 && full_hi >= full_lo;
-            const uint32_t s_head = align;
-            const uint32_t s_tail = (uint32_t)(full_hi - byte0) + align;  // only meaningful when has_tail
-            if (lane == 0) {
-                if (!has_head) a.seam_head[r] = 0;
-                if (!has_tail) a.seam_tail[r] = 0;
-            }
-            // frame word f holds region bits [32f - shift, 32f - shift + 32): image word f - ws shifted right by bs
-            // bits, its top bits coming from the word before.  Two aligned 16-byte shared loads per chunk (the four
-            // image words of the chunk and the four before them: conflict-free), then a warp-uniform choice of which
-            // of the eight words feed which frame word.
-            const uint32_t bs = shift & 31u, ws = shift >> 5;
-            for (uint32_t c = lane; c < n_chunks; c += 32) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(stage + kStageGuard) + c;
-                const uint4 p = src[-1], q = src[0];
-                uint32_t f0, f1, f2, f3;
-                switch (ws) {
-                    case 0:
-                        f0 = __funnelshift_r(q.x, p.w, bs); f1 = __funnelshift_r(q.y, q.x, bs);
-                        f2 = __funnelshift_r(q.z, q.y, bs); f3 = __funnelshift_r(q.w, q.z, bs);
-                        break;
-                    case 1:
-                        f0 = __funnelshift_r(p.w, p.z, bs); f1 = __funnelshift_r(q.x, p.w, bs);
-                        f2 = __funnelshift_r(q.y, q.x, bs); f3 = __funnelshift_r(q.z, q.y, bs);
-                        break;
-                    case 2:
-                        f0 = __funnelshift_r(p.z, p.y, bs); f1 = __funnelshift_r(p.w, p.z, bs);
-                        f2 = __funnelshift_r(q.x, p.w, bs); f3 = __funnelshift_r(q.y, q.x, bs);
-                        break;
-                    default:
-                        f0 = __funnelshift_r(p.y, p.x, bs); f1 = __funnelshift_r(p.z, p.y, bs);
-                        f2 = __funnelshift_r(p.w, p.z, bs); f3 = __funnelshift_r(q.x, p.w, bs);
-                        break;
-                }
-                const uint4 v = make_uint4(bswap32(f0), bswap32(f1), bswap32(f2), bswap32(f3));
-                const uint32_t k0 = c * 16;
-                if (k0 >= s_lo && k0 + 16 <= s_hi) {
-                    st_stream_v4(gbase + k0, v);
-                } else {
-                    // a block at the ragged start or end of the region: bytewise, through a small buffer
-                    uint4 *tmp = reinterpret_cast<uint4 *>(edge + (c == 0 ? 0 : 16));
-                    *tmp = v;
-                    const uint8_t *tb = reinterpret_cast<const uint8_t *>(tmp);
-                    const uint32_t lo_k = max(k0, s_lo), hi_k = min(k0 + 16u, s_hi);
-                    for (uint32_t kk = lo_k; kk < hi_k; ++kk) gbase[kk] = tb[kk - k0];
-                    if (has_head && s_head >= k0 && s_head < k0 + 16u) a.seam_head[r] = tb[s_head - k0];
-                    if (has_tail && s_tail >= k0 && s_tail < k0 + 16u) a.seam_tail[r] = tb[s_tail - k0];
-                }
-            }
-        }
+        region_copy_out(a, r, stage, edge, bit_begin, region_bits, lane);
         __syncwarp();  // everyone has read the image
         if (r_next >= a.n_regions) break;
         r = r_next;
+    }
+}
+
+// ------------------------------------------------------------------ single-pass pack (codes <= 32 bits)
+// ONE pass over the text: the offsets come from a decoupled look-back instead of a first pass.
+// A CTA works on a TILE of `warps` consecutive regions (one warp each), tiles are handed out in order by a ticket:
+//   1. a lane packs the 64 symbols of its run into a PRIVATE bit string in shared memory, from bit 0 of its own
+//      words (no offset needed yet); its length is the run's bit count;
+//   2. warp scan of the run lengths: the lane's bit offset inside the region, the region's bits;
+//   3. the region totals of the tile meet in shared memory (named barrier: the other warps only arrive); warp 0 scans
+//      them, publishes the tile's bit count in its look-back descriptor and walks back over the descriptors of the
+//      tiles before it (aggregates until the first inclusive prefix) - while the other warps do step 4;
+//   4. every lane shifts its private string to its offset inside the warp's region image (funnel shift per word;
+//      whole words are stored, the two words it shares with its neighbours are ORed into zeroed words);
+//   5. barrier; the region's final bit position is the tile's base plus the totals of the warps before: the image goes
+//      out exactly as in the two-pass kernel (region_copy_out).
+// What the look-back costs: one 8-byte descriptor per 32 Ki symbols (16 warps) and, in the steady state, one or two L2
+// round trips per tile, hidden behind step 4.  (The first attempt at this, with 4 Ki-symbol tiles, was limited by the
+// descriptor chain - ~64 tiles/us - to 4 ms/GiB; at CTA-sized tiles the chain needs 33 K steps per GiB instead of 262 K.)
+// MEASURED (r2, text-1G, profiles/r2_kernels.md): 1.93 ms against 0.29 + 0.77 ms for the two passes.  The chain is no
+// longer the limit; the CTA-wide lockstep is (stall_barrier 4.6 per issued instruction, 0.34 IPC per scheduler), and the
+// private strings double a warp's shared memory, which halves the warps per SM.  The two-pass pack therefore stays the
+// default and this kernel is selectable (ET_TUNE_PACK_SINGLE_PASS) - it reads the text once (DRAM 1.09 + 0.58 GB vs
+// 2.17 + 0.63 GB) and would win on a part where HBM, not instruction issue, bounds this path.
+constexpr int kTileMaxWarps = 16;
+struct TileShared {
+    uint32_t region_bits[kTileMaxWarps];
+    unsigned long long tile_base;
+    uint32_t next_tile;
+};
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// Dynamic shared memory: table (32 KiB) | per warp: private strings (32 lanes x priv_stride words) | bit image | 32 edge bytes.
+__global__ void __launch_bounds__(kTileMaxWarps * 32, 1) pack_tiles_kernel(const PackArgs a, uint32_t warps, uint32_t priv_stride, uint32_t n_tiles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ TileShared sh;
+    uint8_t *table = smem;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, threads = warps * 32;
+    const uint32_t warp_words = 32u * priv_stride + a.image_words;
+    uint32_t *priv = reinterpret_cast<uint32_t *>(smem + kTableBytes) + (size_t)warp * warp_words + lane * priv_stride;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + kTableBytes) + (size_t)warp * warp_words + 32u * priv_stride;
+    uint8_t *edge = smem + kTableBytes + (size_t)warps * warp_words * 4 + warp * 32;
+    {
+        const uint2 *src = static_cast<const uint2 *>(a.tables);
+        uint2 *dst = reinterpret_cast<uint2 *>(table);
+        for (uint32_t i = tid; i < 256 * kTableLanes; i += threads) dst[i] = src[i / kTableLanes];
+        for (uint32_t i = lane; i < a.image_words; i += 32) stage[i] = 0;
+        if (tid == 0) sh.next_tile = atomicAdd(a.ticket, 1u);
+    }
+    __syncthreads();
+    const uint8_t *table_lane = table + (lane & (kTableLanes - 1)) * 8;
+    const uint32_t priv_bit0 = (uint32_t)__cvta_generic_to_shared(priv) * 8u;
+
+    for (;;) {
+        const uint32_t tile = sh.next_tile;
+        if (tile >= n_tiles) break;
+        const uint32_t r = tile * warps + warp;
+        const bool live = r < a.n_regions;
+        // ---- 1. the run into the lane's private string
+        uint32_t my_bits = 0;
+        if (live) {
+            const bool interior = region_is_interior(a, r);
+            uint4 raw[4];
+            unsigned long long valid;
+            load_run(a, r, lane, interior, raw, &valid);
+            BitAcc acc;
+            acc.hi = acc.lo = 0;
+            acc.pos = priv_bit0;
+            pack_run_symbols(acc, raw, valid, interior, table_lane);
+            my_bits = acc.pos - priv_bit0;
+            if (my_bits & 31u) priv[my_bits >> 5] = acc.lo << (32u - (my_bits & 31u));  // the unfinished last word, zero padded
+        }
+        // ---- 2. offsets inside the region
+        const uint32_t incl = warp_inclusive_scan(my_bits, lane);
+        const uint32_t region_bits = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t my_off = incl - my_bits;
+        if (lane == 0) sh.region_bits[warp] = region_bits;
+        // ---- 3. the tile's bit count meets the tiles before it (warp 0), the others go on
+        if (warp != 0) {
+            named_bar_arrive(1, (int)threads);
+        } else {
+            named_bar_sync(1, (int)threads);
+            uint32_t mine = lane < warps ? sh.region_bits[lane] : 0u;
+            const uint32_t tile_bits = __reduce_add_sync(0xffffffffu, mine);
+            unsigned long long start;
+            if (tile == 0) {
+                start = a.bit_phase;
+            } else {
+                if (lane == 0) st_relaxed_u64(a.tile_desc + tile, kStatusAggregate | tile_bits);
+                start = lookback_exclusive(a.tile_desc, tile, lane);
+            }
+            if (lane == 0) {
+                st_relaxed_u64(a.tile_desc + tile, kStatusPrefix | (start + tile_bits));
+                sh.tile_base = start;
+                sh.next_tile = atomicAdd(a.ticket, 1u);  // every warp has read the current one: it arrived at barrier 1
+            }
+        }
+        // ---- 4. private strings to their place in the region image
+        if (live) {
+            const uint32_t w0 = my_off >> 5, s = my_off & 31u, n_w = (my_bits + 31u) >> 5;
+            const uint32_t w_last = (my_off + my_bits) >> 5;  // the word after the lane's last bit may be this one too
+            uint32_t *img = stage + kStageGuard;
+            // words shared with the neighbours (and the two after the region's end, which the copy-out reads) start from zero
+            if (my_bits) {
+                img[w0] = 0;
+                img[w_last] = 0;
+            }
+            if (lane < 2) img[(region_bits >> 5) + lane] = 0;
+            __syncwarp();
+            uint32_t prev = 0;
+            for (uint32_t j = 0; j <= n_w && my_bits; ++j) {
+                const uint32_t cur = j < n_w ? priv[j] : 0u;
+                const uint32_t v = __funnelshift_r(cur, prev, s);  // (prev:cur) >> s: the low s bits of prev on top of cur's high bits
+                prev = cur;
+                if (j == 0 || w0 + j >= w_last) {
+                    if (v) atomicOr(img + w0 + j, v);
+                } else {
+                    img[w0 + j] = v;
+                }
+            }
+        }
+        // ---- 5. the tile's base is known: out it goes
+        named_bar_sync(2, (int)threads);
+        if (live) {
+            unsigned long long bit_begin = sh.tile_base;
+            for (uint32_t q = 0; q < warp; ++q) bit_begin += sh.region_bits[q];
+            if (lane == 0) a.tile_state[r] = bit_begin + region_bits;  // for the seam fix-up
+            region_copy_out(a, r, stage, edge, bit_begin, region_bits, lane);
+        }
+        named_bar_sync(3, (int)threads);  // sh.region_bits and sh.tile_base may be overwritten; next_tile is settled
     }
 }
 
@@ -693,7 +840,7 @@ PackScratch pack_scratch_carve(void *base, uint32_t num_tiles) {
 
 cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint32_t max_len, uint8_t *d_out, uint32_t bit_phase,
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
-                        cudaStream_t stream, int *launches) {
+                        cudaStream_t stream, int *launches, bool single_pass) {
     if (g.num_tiles == 0) return cudaSuccess;
     cudaError_t err = cudaSuccess;
     PackArgs a;
@@ -708,6 +855,7 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
     a.seam_head = s.seam_head;
     a.seam_tail = s.seam_tail;
     a.ticket = s.ticket;
+    a.tile_desc = nullptr;
     a.tile_bits = s.tile_bits;
     a.group_prefix = s.group_prefix;
     a.group_tiles = 1;
@@ -749,6 +897,34 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         a.interior_hi = (uint32_t)(g.v_end / kRegionSyms);
         if (a.interior_hi < a.interior_lo) a.interior_hi = a.interior_lo;
         a.image_words = (uint32_t)(kStageGuard + (kRegionSyms * max_len + 31) / 32 + 16 + 3) & ~3u;
+        if (single_pass) {
+            // single pass: tiles of `warps` regions, look-back descriptors where the two-pass path keeps its run totals
+            const uint32_t priv_stride = (2u * max_len + 1u) | 1u;  // words of a lane's private string (64 codes), odd: lanes never share a bank at equal depth
+            const uint32_t warp_bytes = (32u * priv_stride + a.image_words) * 4u + 32u;
+            int max_smem = 0, dev = 0;
+            if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+            if ((err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
+            uint32_t warps = ((uint32_t)max_smem - (uint32_t)kTableBytes - 1024u) / warp_bytes;
+            if (warps > (uint32_t)kTileMaxWarps) warps = kTileMaxWarps;
+            if (warps > 4) warps &= ~3u;
+            if (warps >= 1) {
+                const uint32_t n_tiles = (n_regions + warps - 1) / warps;
+                a.tile_desc = reinterpret_cast<unsigned long long *>(a.run_bits);  // [n_tiles] <= 8 B per region: inside the run-total area (64 B per region)
+                if ((err = cudaMemsetAsync(rs.ticket, 0, 16, stream)) != cudaSuccess) return err;
+                if ((err = cudaMemsetAsync(a.tile_desc, 0, (size_t)n_tiles * 8, stream)) != cudaSuccess) return err;
+                const int smem = kTableBytes + (int)(warps * warp_bytes);
+                if ((err = cudaFuncSetAttribute(pack_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return err;
+                unsigned grid = (unsigned)num_sms * (2u * (unsigned)smem + 2048u <= (unsigned)max_smem ? 2u : 1u);
+                if (grid > n_tiles) grid = n_tiles;
+                a.ticket = rs.ticket;
+                pack_tiles_kernel<<<grid, warps * 32, smem, stream>>>(a, warps, priv_stride, n_tiles);
+                if (launches) *launches += 1;
+                if ((err = cudaGetLastError()) != cudaSuccess) return err;
+                seam_fixup_kernel<<<(n_regions + 255) / 256, 256, 0, stream>>>(a.tile_state, a.seam_head, a.seam_tail, n_regions, bit_phase, d_out);
+                if (launches) *launches += 1;
+                return cudaGetLastError();
+            }
+        }
         a.group_tiles = pack_group_tiles(n_regions);
         if (a.group_tiles < 2) a.group_tiles = 2;
         for (a.group_shift = 0; (1u << a.group_shift) < a.group_tiles; ++a.group_shift) {}

@@ -58,6 +58,23 @@ def test_encode_matches_oracle_on_cases(codec):
         assert out.tobytes() == _oracle_et(data), name
 
 
+def test_single_pass_pack_matches_the_two_pass_and_the_oracle(codec, manifest):
+    # the encoder packs in two passes (run totals, then pack); the single pass with a decoupled look-back over tile
+    # descriptors stays selectable (measured slower: DESIGN.md) - both must give the oracle's bytes
+    thr = synth.thresholds_from_weights(synth.text_weights(manifest["midsummer_histogram"]))
+    cases = dict(make_cases())
+    cases["text_3M"] = synth.generate((3 << 20) + 77, thr)
+    try:
+        for mode in (1, 0):
+            codec.set_tuning(_abi.TUNE_PACK_SINGLE_PASS, mode)
+            for name, data in cases.items():
+                want = _oracle_et(data)
+                n, enc = codec.encode(data, et.EncodeFlags(write_output=True, no_scratch_limit=True))
+                assert enc.tobytes() == want, (mode, name)
+    finally:
+        codec.set_tuning(_abi.TUNE_PACK_SINGLE_PASS, 0)
+
+
 def test_encode_dry_run_returns_size_only(codec, fixtures, manifest):
     n, out = codec.encode(fixtures["nice.shakespeare.txt"], et.EncodeFlags(write_output=False))
     assert n == 374 and out is None  # encode.zig:319,336; README.md:51
