@@ -313,6 +313,7 @@ extern "C" int et_ctx_set_tuning(et_ctx *ctx, int key, long long value) {
         case ET_TUNE_LANE_MIN_BYTES: ctx->tune.lane_min_bytes = value; return ET_OK;
         case ET_TUNE_DEBUG: ctx->tune.debug = value != 0; return ET_OK;
         case ET_TUNE_SYNC_WARPS: ctx->tune.sync_warps = (int)value; return ET_OK;
+        case ET_TUNE_NO_TRANSFER: ctx->tune.no_transfer = value != 0; return ET_OK;
         case ET_TUNE_PACK_SINGLE_PASS: ctx->tune.pack_single_pass = value != 0; return ET_OK;
     }
     return fail(ctx, ET_ERR_INVALID_ARG, "unknown tuning key %d", key);
@@ -530,7 +531,8 @@ int unpack_dev(et_ctx *ctx, const UnpackGeometry &g, const et_dictionary &dict, 
     uint32_t rounds = 0;
     const uint16_t *d_slots = reinterpret_cast<const uint16_t *>(ctx->d_small + kOffSlots);
     ET_CUDA(ctx, launch_unpack(g, chunk_bytes, d_clut, d_wlut, d_nodes, d_slots, d_out, max_symbols, ctx->d_scratch,
-                               ctx->h_small + kOffFlags, s, ctx->tune, ctx->fixed_len, &launches, &rounds));
+                               ctx->h_small + kOffFlags, s, ctx->tune, ctx->fixed_len,
+                               (dict.max_length - dict.min_length <= 2 && dict.max_length <= 16) ? dict.max_length : 0u, &launches, &rounds));
     ctx->launches += (uint64_t)launches;
     ctx->last_decode_rounds = rounds;
     // launch_unpack left the stream idle and a copy of the scratch header in the pinned block:

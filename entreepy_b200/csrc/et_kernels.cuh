@@ -77,6 +77,7 @@ struct UnpackTuning {
     int max_smem = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int num_sms = 0;
     int sync_warps = 0;             // > 0: warps per CTA of the count walk (default: as many as fit)
+    int no_transfer = 0;            // non-zero: slowly synchronising codes take the repair rounds instead of transfer functions
     int pack_single_pass = 0;       // non-zero: the encoder packs in ONE pass with a decoupled look-back (measured slower, see et_pack.cu)
     void *d_lane_tables = nullptr;  // device-built tables of the lane-interleaved decoder
 };
@@ -94,10 +95,13 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes);
 // *rounds_out = passes over the chunk entries it took (2 = the guesses plus one repair round sufficed).
 // fixed_len: the dictionary is a complete code whose codes all have this many bits (0: it is not) — such a
 // stream never re-synchronises, but every chunk's entry follows from the first one in closed form.
+// transfer_states: > 0 for codes that synchronise slowly (lengths within 2 bits of each other): the number of bit
+// offsets at which a chunk can be entered (= the longest code); the per-thread path then tabulates every chunk's
+// transfer function and scans instead of running repair rounds.
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
                           const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
-                          uint8_t *h_hdr, cudaStream_t stream, const UnpackTuning &tune, uint32_t fixed_len, int *launches,
-                          uint32_t *rounds_out);
+                          uint8_t *h_hdr, cudaStream_t stream, const UnpackTuning &tune, uint32_t fixed_len, uint32_t transfer_states,
+                          int *launches, uint32_t *rounds_out);
 
 // ---------------------------------------------------------------- synthetic input generator
 cudaError_t launch_synth(uint8_t *d_out, size_t n, uint64_t seed, uint64_t first_index, const uint32_t *d_thresholds,

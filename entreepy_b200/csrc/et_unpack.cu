@@ -72,6 +72,8 @@ struct DecArgs {
     uint32_t *error_flags;
     unsigned long long *total;
     uint32_t *entry_exit;
+    uint8_t *tr_exit;             // [n << s_log2] transfer functions of the chunks: exit for every possible entry (slowly synchronising codes)
+    uint16_t *tr_cnt;             // [n << s_log2] ... and the symbols
     unsigned long long *dbg;      // ET_TUNE_DEBUG: per CTA {smid, start ns, end ns} of the two big lane kernels (or null)
     uint8_t *out;
     uint64_t max_symbols;
@@ -320,9 +322,14 @@ struct WordReader {
 // Decode from absolute bit `pos` every symbol that begins before `own_end`; nothing may end
 // after `hard_end` (the end of the stream).  Returns the position reached.  WRITE stores the
 // symbols at out[o..) while o < max_symbols.
+// clut / wlut: the first-level tables to read - the global ones (a.clut, a.wlut) or a copy in shared memory where the
+// caller has one (a walk through L2-resident tables costs ~10x the latency per symbol).
 template <bool WRITE>
 __device__ __noinline__ uint64_t walk_generic(const DecArgs &a, uint64_t pos, uint64_t own_end, uint64_t hard_end,
-                                              uint32_t *count, uint64_t o, uint32_t *bad) {
+                                              uint32_t *count, uint64_t o, uint32_t *bad, const uint32_t *clut = nullptr,
+                                              const uint32_t *wlut = nullptr) {
+    if (!clut) clut = a.clut;
+    if (!wlut) wlut = a.wlut;
     uint32_t n = 0;
     uint64_t wi = pos >> 5;
     WordReader rd;
@@ -337,8 +344,8 @@ __device__ __noinline__ uint64_t walk_generic(const DecArgs &a, uint64_t pos, ui
         }
         const uint32_t win = __funnelshift_l(lo, hi, (uint32_t)pos & 31u);
         const uint32_t idx = win >> (32 - kLutBits);
-        const uint32_t c = __ldg(a.clut + idx);
-        uint32_t len = (c >> 16) & 0xffu, sym = __ldg(a.wlut + idx) & 0xffu;
+        const uint32_t c = clut[idx];
+        uint32_t len = (c >> 16) & 0xffu, sym = WRITE ? (wlut[idx] & 0xffu) : 0u;
         if (c & kLutMarker) {
             len = long_code(win, __ldg(a.wlut + idx) & 0xffffu, a.nodes, &sym);
             if (len == 0) {  // no code here (incomplete dictionary): skip one bit, like the fast walkers
@@ -363,6 +370,7 @@ __device__ __noinline__ uint64_t walk_generic(const DecArgs &a, uint64_t pos, ui
 struct Chunk {
     uint64_t begin, end;  // bits; end is clipped to own_end_bit
     bool interior;        // every piece, the piece before and the piece after are plain readable stream
+    bool walkable;        // every piece and the piece after can be loaded whole: the fast walkers may run from a KNOWN start
 };
 __device__ __forceinline__ Chunk chunk_of(const DecArgs &a, uint32_t c) {
     Chunk k;
@@ -370,8 +378,11 @@ __device__ __forceinline__ Chunk chunk_of(const DecArgs &a, uint32_t c) {
     k.begin = a.grid_bit + (uint64_t)c * bits;
     const uint64_t e = k.begin + bits;
     k.end = e < a.own_end_bit ? e : a.own_end_bit;
-    k.interior = e <= a.own_end_bit && e + 128 <= a.end_bit && (e >> 3) + 16 <= a.byte_hi &&
-                 (k.begin >> 3) >= a.byte_lo + 16 && k.begin >= a.grid_bit + 256;
+    k.walkable = e <= a.own_end_bit && e + 128 <= a.end_bit && (e >> 3) + 16 <= a.byte_hi;
+    k.interior = k.walkable && (k.begin >> 3) >= a.byte_lo + 16 && k.begin >= a.grid_bit + 256;
+    // (a stream that starts inside the first 16-byte piece of chunk 0 - byte_lo < 16 - shares that piece with whatever
+    // precedes it in the caller's buffer: the same aligned 16 bytes, so loading it whole cannot fault, and a walk from
+    // the known start never looks at the bits before it)
     return k;
 }
 
@@ -438,11 +449,11 @@ __device__ __forceinline__ uint32_t count_chunk_fast(const DecArgs &a, const Chu
     return c;
 }
 
-__global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecArgs a, int round) {
+__global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecArgs a, int round, uint32_t only_below = 0xFFFFFFFFu) {
     __shared__ __align__(16) uint32_t clut_sh[kLutSize];
     const uint32_t c = blockIdx.x * kChunkThreads + threadIdx.x;
     uint32_t start = 0;
-    bool work = c < a.n_chunks;
+    bool work = c < a.n_chunks && c < only_below;
     if (work && round != 0) {
         if (c == 0) {
             work = false;
@@ -468,7 +479,7 @@ __global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecA
         known = true;
     }
     uint32_t cnt = 0, entry = start, exit_bits = 0;
-    if (k.interior) {
+    if (k.interior || (known && k.walkable && start < 256u)) {
         const uint32_t s = count_chunk_fast(a, k, start, !known, smem_addr(clut_sh), &entry);
         cnt = s >> 9;
         exit_bits = s & kPosMask;
@@ -476,16 +487,139 @@ __global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecA
         uint64_t pos = k.begin + start;
         uint32_t bad = 0, dummy = 0;
         if (!known && k.begin >= a.byte_lo * 8 + 128) {  // same run-up as the fast path
-            pos = walk_generic<false>(a, k.begin - 128, k.begin, a.end_bit, &dummy, 0, &bad);
+            pos = walk_generic<false>(a, k.begin - 128, k.begin, a.end_bit, &dummy, 0, &bad, clut_sh);
             if (pos < k.begin) pos = k.begin;
         }
         entry = (uint32_t)(pos - k.begin);
-        if (pos < k.end) pos = walk_generic<false>(a, pos, k.end, a.end_bit, &cnt, 0, &bad);
+        if (pos < k.end) pos = walk_generic<false>(a, pos, k.end, a.end_bit, &cnt, 0, &bad, clut_sh);
         exit_bits = pos > k.end ? (uint32_t)(pos - k.end) : 0u;
     }
     a.start_off[c] = (uint16_t)entry;
     a.exit_off[c] = (uint16_t)exit_bits;
     a.count[c] = cnt;
+}
+
+// ------------------------------------------------------------------ transfer functions (slowly synchronising codes)
+// Codes whose lengths are nearly equal (uniform bytes: 7 and 8 bits) re-synchronise after kilobytes, sometimes after
+// a hundred: the repair rounds above then walk the longest unsynchronised stretch one chunk per round, a sequential
+// dependency no amount of parallel hardware shortens.  But a chunk can only be ENTERED at max_len different bit
+// offsets (the first codeword boundary at or after its first bit lies less than one code past it), so its effect is a
+// function from at most max_len entries to (exit, symbols).  One thread per (chunk, entry) tabulates it; composing the
+// functions left to right is associative, so the true entry of every chunk comes out of a scan - no rounds, no luck.
+// The cost is max_len count walks instead of one (8 for byte-uniform data), all of them parallel.
+constexpr uint32_t kMaxStates = 16;
+__global__ void __launch_bounds__(kChunkThreads, 6) chunk_transfer_kernel(const DecArgs a, uint32_t s_log2, uint32_t n_states) {
+    __shared__ __align__(16) uint32_t clut_sh[kLutSize];
+    for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) clut_sh[i] = a.clut[i];
+    __syncthreads();
+    const uint32_t idx = (gridDim.x - 1u - blockIdx.x) * kChunkThreads + threadIdx.x;  // last chunks first: the stream's ragged end is the slow one
+    const uint32_t c = idx >> s_log2, e = idx & ((1u << s_log2) - 1u);
+    if (c == 0 || c >= a.n_chunks || e >= n_states) return;  // chunk 0 is entered at the head: chunk_sync_kernel walks it
+    const Chunk k = chunk_of(a, c);
+    uint32_t cnt = 0, exit_bits = 0;
+    if (k.walkable) {
+        uint32_t entry;
+        const uint32_t s = count_chunk_fast(a, k, e, false, smem_addr(clut_sh), &entry);
+        cnt = s >> 9;
+        exit_bits = s & kPosMask;
+    } else {
+        uint64_t pos = k.begin + e;
+        uint32_t bad = 0;
+        if (pos < k.end) pos = walk_generic<false>(a, pos, k.end, a.end_bit, &cnt, 0, &bad, clut_sh);
+        exit_bits = pos > k.end ? (uint32_t)(pos - k.end) : 0u;
+    }
+    a.tr_exit[idx] = (uint8_t)(exit_bits < n_states ? exit_bits : 0xFFu);  // 0xFF cannot be composed: the final check then fails and the rounds take over
+    a.tr_cnt[idx] = (uint16_t)cnt;
+}
+
+// Maps are 16 nibbles in a 64-bit word (entry e -> nibble e).  The scan of the chunks' functions, three kernels:
+//   compose_segments  every thread composes the functions of kSegChunks consecutive chunks, a block-wide scan composes
+//                     the segments of the block (exclusive prefix per thread, total per block);
+//   compose_blocks    one block scans the block totals;
+//   compose_apply     every thread enters its segment with the true entry in hand and writes what the repair rounds
+//                     would have settled on: start_off, exit_off, count.
+constexpr uint32_t kSegChunks = 16, kSegThreads = 256;
+constexpr unsigned long long kIdentMap = 0xFEDCBA9876543210ull;
+__device__ __forceinline__ unsigned long long map_then(unsigned long long first, unsigned long long second, uint32_t n_states) {
+    unsigned long long out = 0;
+    for (uint32_t e = 0; e < n_states; ++e) {
+        const uint32_t x = (uint32_t)(first >> (4 * e)) & 15u;
+        out |= ((second >> (4 * x)) & 15ull) << (4 * e);
+    }
+    return out;
+}
+// The chunk's function as a nibble map (an exit that is no state maps to 0: caught by the final check).
+__device__ __forceinline__ unsigned long long row_map(const DecArgs &a, uint32_t c, uint32_t s_log2, uint32_t n_states) {
+    unsigned long long m = 0;
+    const uint8_t *row = a.tr_exit + ((size_t)c << s_log2);
+    if (s_log2 >= 3) {  // rows of 8 or 16 bytes: one or two 8-byte loads
+        for (uint32_t h = 0; h < (1u << (s_log2 - 3)); ++h) {
+            const unsigned long long v = *reinterpret_cast<const unsigned long long *>(row + 8 * h);
+            for (uint32_t e = 0; e < 8 && 8 * h + e < n_states; ++e) m |= ((v >> (8 * e)) & 15ull) << (4 * (8 * h + e));
+        }
+    } else {
+        for (uint32_t e = 0; e < n_states; ++e) m |= (unsigned long long)(row[e] & 15u) << (4 * e);
+    }
+    return m;
+}
+// seg_prefix[t]: composition of the segments before thread t inside its block; block_map[b]: the whole block.
+__global__ void __launch_bounds__(kSegThreads) compose_segments_kernel(const DecArgs a, uint32_t s_log2, uint32_t n_states,
+                                                                       unsigned long long *seg_prefix, unsigned long long *block_map) {
+    __shared__ unsigned long long maps[kSegThreads];
+    const uint32_t t = threadIdx.x, g = blockIdx.x * kSegThreads + t;
+    const uint32_t lo = max(min(g * kSegChunks, a.n_chunks), 1u), hi = max(min(g * kSegChunks + kSegChunks, a.n_chunks), 1u);  // chunk 0 is entered at the head
+    unsigned long long m = kIdentMap;
+    for (uint32_t c = lo; c < hi; ++c) m = map_then(m, row_map(a, c, s_log2, n_states), n_states);
+    maps[t] = m;
+    __syncthreads();
+    for (int d = 1; d < (int)kSegThreads; d <<= 1) {  // inclusive scan: maps[t] = segments 0..t of the block, left to right
+        const unsigned long long left = t >= (uint32_t)d ? maps[t - d] : kIdentMap;
+        __syncthreads();
+        maps[t] = map_then(left, maps[t], n_states);
+        __syncthreads();
+    }
+    seg_prefix[g] = t ? maps[t - 1] : kIdentMap;
+    if (t == kSegThreads - 1) block_map[blockIdx.x] = maps[t];
+}
+__global__ void __launch_bounds__(1024) compose_blocks_kernel(uint32_t n_blocks, uint32_t n_states, unsigned long long *block_map) {
+    // exclusive scan of the block maps, in place: thread t composes a run of them, a block-wide scan composes the runs
+    __shared__ unsigned long long maps[1024];
+    const uint32_t t = threadIdx.x, per = (n_blocks + 1023u) / 1024u;
+    const uint32_t lo = min(t * per, n_blocks), hi = min(lo + per, n_blocks);
+    unsigned long long m = kIdentMap;
+    for (uint32_t b = lo; b < hi; ++b) m = map_then(m, block_map[b], n_states);
+    maps[t] = m;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long left = t >= (uint32_t)d ? maps[t - d] : kIdentMap;
+        __syncthreads();
+        maps[t] = map_then(left, maps[t], n_states);
+        __syncthreads();
+    }
+    unsigned long long run = t ? maps[t - 1] : kIdentMap;
+    for (uint32_t b = lo; b < hi; ++b) {
+        const unsigned long long mb = block_map[b];
+        block_map[b] = run;
+        run = map_then(run, mb, n_states);
+    }
+}
+__global__ void __launch_bounds__(kSegThreads) compose_apply_kernel(const DecArgs a, uint32_t s_log2, uint32_t n_states,
+                                                                    const unsigned long long *seg_prefix, const unsigned long long *block_map) {
+    const uint32_t g = blockIdx.x * kSegThreads + threadIdx.x;
+    const uint32_t lo = max(min(g * kSegChunks, a.n_chunks), 1u), hi = max(min(g * kSegChunks + kSegChunks, a.n_chunks), 1u);
+    if (lo >= hi) return;
+    uint32_t e = a.exit_off[0];  // where chunk 0 (walked from the head) leaves the stream
+    if (e >= n_states) e = 0;
+    e = (uint32_t)(block_map[blockIdx.x] >> (4 * e)) & 15u;
+    e = (uint32_t)(seg_prefix[g] >> (4 * e)) & 15u;
+    for (uint32_t c = lo; c < hi; ++c) {
+        const size_t i = ((size_t)c << s_log2) + e;
+        const uint32_t x = a.tr_exit[i];
+        a.start_off[c] = (uint16_t)e;
+        a.exit_off[c] = (uint16_t)(x < n_states ? x : 0u);
+        a.count[c] = a.tr_cnt[i];
+        e = x < n_states ? x : 0u;
+    }
 }
 
 // ------------------------------------------------------------------ scan
@@ -544,7 +678,8 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
     for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) wlut_sh[i] = a.wlut[i];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t c = blockIdx.x * kChunkThreads + tid;
+    const uint32_t bid = gridDim.x - 1u - blockIdx.x;  // last chunks first: the stream's ragged end (walked with every check) is the slow one
+    const uint32_t c = bid * kChunkThreads + tid;
     const bool live = c < a.n_chunks;
     const uint32_t cnt = live ? a.count[c] : 0u;
     // where this chunk's text goes: block prefix + exclusive scan inside the block
@@ -558,13 +693,13 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
     __syncthreads();
     uint32_t before = 0;
     for (uint32_t q = 0; q < warp; ++q) before += warp_sum[q];
-    const unsigned long long o = a.block_prefix[blockIdx.x] + before + (incl - cnt);
+    const unsigned long long o = a.block_prefix[bid] + before + (incl - cnt);
     if (!live || cnt == 0 || o >= a.max_symbols) return;
 
     const Chunk k = chunk_of(a, c);
     const uint32_t start = a.start_off[c];
     uint32_t bad = 0;
-    if (k.interior && o + cnt <= a.max_symbols) {
+    if ((k.interior || (k.walkable && start < 256u)) && o + cnt <= a.max_symbols) {
         uint8_t *dst = a.out + o;
         OutRing r;
         r.ring_s = smem_addr(rings) + warp * 2048u + lane * 4u;
@@ -604,7 +739,7 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
             r.gsector[kk & 31u] = (uint8_t)lds_u8(ring_slot(r, kk >> 2) + (kk & 3u));
     } else {
         uint32_t n = 0;
-        if (k.begin + start < k.end) walk_generic<true>(a, k.begin + start, k.end, a.end_bit, &n, o, &bad);
+        if (k.begin + start < k.end) walk_generic<true>(a, k.begin + start, k.end, a.end_bit, &n, o, &bad, nullptr, wlut_sh);
     }
     if (bad) atomicOr(a.error_flags, kErrInvalidCode);
 }
@@ -684,6 +819,13 @@ uint32_t unpack_chunk_bytes(const UnpackGeometry &g, const UnpackTuning &tune, u
     const uint64_t bytes = (g.own_end_bit - g.own_begin_bit + 7) / 8;
     const uint32_t spread = max_length - min_length;
     if (spread > 2 && bytes >= lane_path_min_bytes(tune)) return kLaneBytes;  // lane-interleaved decoder
+    if (spread <= 2 && max_length <= kMaxStates) {
+        // slowly synchronising codes go through transfer functions (max_length walks per chunk, all parallel); the write
+        // walk is one thread per chunk, so short chunks keep the GPU full
+        uint32_t cb = 512u;
+        while (cb > 256u && bytes / cb * max_length < (uint64_t)num_sms * 4096) cb >>= 1;
+        return cb;
+    }
     uint32_t cb = spread <= 1 ? 4096u : spread == 2 ? 1024u : 256u;
     const uint32_t floor_cb = cb > 256u ? 256u : 32u;
     while (cb > floor_cb && bytes / cb < (uint64_t)num_sms * 2048) cb >>= 1;
@@ -695,7 +837,9 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t per = chunk_bytes == kLaneBytes ? 32 : kChunkThreads;  // chunks per scanned sum
     const uint64_t nb = (n + per - 1) / per;
     const uint64_t ng = (nb + kGroupRegions - 1) / kGroupRegions;
-    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 4) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * 4 + 64;
+    // exit (u8) and symbols (u16) per (chunk, entry); a map per segment of chunks and per block of segments
+    const size_t transfer = chunk_bytes == kLaneBytes ? 0 : (size_t)n * kMaxStates * 3 + 64 + ((size_t)n / kSegChunks + 2 * kSegThreads + 64) * 8;
+    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 4) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * 4 + 64 + transfer;
 }
 
 // Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
@@ -801,8 +945,8 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
 
 cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const uint32_t *d_clut, const uint32_t *d_wlut,
                           const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
-                          uint8_t *h_hdr, cudaStream_t stream, const UnpackTuning &tune, uint32_t fixed_len, int *launches,
-                          uint32_t *rounds_out) {
+                          uint8_t *h_hdr, cudaStream_t stream, const UnpackTuning &tune, uint32_t fixed_len, uint32_t transfer_states,
+                          int *launches, uint32_t *rounds_out) {
     uint32_t *h_flag = reinterpret_cast<uint32_t *>(h_hdr + 32);  // a word for the check rounds
     const uint64_t n64 = chunk_count(g, chunk_bytes);
     uint8_t *p = static_cast<uint8_t *>(scratch_base);
@@ -849,6 +993,8 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 12 + 63) & ~(size_t)63));
     a.work = reinterpret_cast<uint32_t *>(a.group_prefix + (nb + 1023) / 1024 + 1);
     a.work_count = reinterpret_cast<uint32_t *>(p + 32);
+    a.tr_exit = reinterpret_cast<uint8_t *>(a.work) + (((size_t)nb * 4 + 64 + 63) & ~(size_t)63);
+    a.tr_cnt = reinterpret_cast<uint16_t *>(a.tr_exit + (size_t)n * kMaxStates);
     a.out = d_out;
     a.max_symbols = max_symbols;
     a.dbg = nullptr;
@@ -861,12 +1007,31 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     // chunk), the final check fused into the block sums, the write walk — and a single look at
     // the flag at the very end.  Only when that check failed (slowly synchronising codes) do
     // the fixpoint rounds run, and the sums and the write walk are repeated.
-    chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, 0);
-    chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, 1);
+    const bool transfer = transfer_states >= 2 && transfer_states <= kMaxStates && !fixed_len && n > 1 && !tune.no_transfer;
+    uint32_t rounds = 2;
+    if (transfer) {
+        // slowly synchronising codes: the chunks' transfer functions and a scan instead of repair rounds
+        uint32_t s_log2 = 1;
+        while ((1u << s_log2) < transfer_states) ++s_log2;
+        chunk_sync_kernel<<<1, kChunkThreads, 0, stream>>>(a, 0, 1u);  // chunk 0 from the head (or from its guess, for a shard)
+        const uint64_t threads = (uint64_t)n << s_log2;
+        chunk_transfer_kernel<<<(unsigned)((threads + kChunkThreads - 1) / kChunkThreads), kChunkThreads, 0, stream>>>(a, s_log2, transfer_states);
+        const uint32_t seg_blocks = (n + kSegChunks * kSegThreads - 1) / (kSegChunks * kSegThreads);
+        unsigned long long *seg_prefix = reinterpret_cast<unsigned long long *>(a.tr_cnt + ((size_t)n << s_log2)) ;
+        seg_prefix = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(seg_prefix) + 7) & ~(uintptr_t)7);
+        unsigned long long *block_map = seg_prefix + (size_t)seg_blocks * kSegThreads;
+        compose_segments_kernel<<<seg_blocks, kSegThreads, 0, stream>>>(a, s_log2, transfer_states, seg_prefix, block_map);
+        compose_blocks_kernel<<<1, 1024, 0, stream>>>(seg_blocks, transfer_states, block_map);
+        compose_apply_kernel<<<seg_blocks, kSegThreads, 0, stream>>>(a, s_log2, transfer_states, seg_prefix, block_map);
+        if (launches) *launches += 5;
+        rounds = 1;
+    } else {
+        chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, 0);
+        chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, 1);
+        if (launches) *launches += 2;
+    }
     err = cudaMemsetAsync(a.changed, 0, 4, stream);
     if (err != cudaSuccess) return err;
-    if (launches) *launches += 2;
-    uint32_t rounds = 2;
     // Fixpoint rounds, four per host visit (the flag is cleared before the last of them: a round
     // that changed nothing is the proof).
     auto settle = [&]() -> cudaError_t {
@@ -887,7 +1052,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     };
     // Long chunks were chosen because this code synchronises slowly: the guesses are known to be
     // poor, so settle the entries before spending a write walk on them.
-    if (chunk_bytes > 256u && !fixed_len) {
+    if (chunk_bytes > 256u && !fixed_len && !transfer) {
         err = settle();
         if (err != cudaSuccess) return err;
     }

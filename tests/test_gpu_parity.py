@@ -265,16 +265,33 @@ def test_round_trip_text_16m_property(codec, manifest):
 
 
 # ---------------------------------------------------------------- check rounds (streams that do not re-synchronise quickly)
-def test_slow_synchronising_streams_need_fixpoint_rounds_and_still_decode(codec):
-    # 255 equiprobable symbols: 7- and 8-bit codes only; a wrong start survives for kilobytes, so the
-    # guessed chunk entries are wrong and the check rounds must repair them
+def test_slow_synchronising_streams_need_no_rounds_with_transfer_functions(codec):
+    # 255 equiprobable symbols: 7- and 8-bit codes only; a wrong start survives for kilobytes, so guessed chunk entries are
+    # wrong.  The decoder tabulates every chunk's transfer function (exit and symbols for each
+    # of the <= max_len possible entries) and scans them: no repair rounds.  The rounds (round 1's way, still the fallback
+    # when the final check fails) stay selectable and must agree.
     rng = np.random.default_rng(3)
-    for n in (70000, (1 << 22) + 11):
+    for n in (70000, (1 << 22) + 11, (1 << 25) + 3):
         data = rng.integers(1, 256, n, dtype=np.uint8)
         stream = _oracle_et(data)[4:]
         m, out = codec.decode(stream)
         assert m == n and out.tobytes() == data.tobytes()
-        assert codec.last_decode_rounds > 2
+        assert codec.last_decode_rounds <= 2
+        if n < (1 << 25):
+            codec.set_tuning(_abi.TUNE_NO_TRANSFER, 1)
+            try:
+                m, out = codec.decode(stream)
+                assert m == n and out.tobytes() == data.tobytes()
+                assert codec.last_decode_rounds > 2
+            finally:
+                codec.set_tuning(_abi.TUNE_NO_TRANSFER, 0)
+    # lengths 5..7 (spread 2) and a body that does not start on a 16-byte boundary
+    data = rng.choice(np.arange(40, dtype=np.uint8), 3_000_017, p=np.r_[np.full(24, 2.0), np.full(16, 1.0)] / 64.0)
+    stream = _oracle_et(data)[4:]
+    d = et.parse_header(stream)
+    assert d.max_length - d.min_length <= 2
+    m, out = codec.decode(stream)
+    assert m == data.size and out.tobytes() == data.tobytes() and codec.last_decode_rounds <= 2
     # text re-synchronises within a few symbols: the first check round finds nothing to repair
     text = rng.choice(np.frombuffer(b"etaoin shrdlu\n,.", dtype=np.uint8), 1 << 22)
     m, out = codec.decode(_oracle_et(text)[4:])
