@@ -295,15 +295,40 @@ class ManyGpus:
         import torch
 
         h_range, h_text = h_pair
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream()
         inp[: self.plan.n_local].copy_(h_in, non_blocking=True)
-        res = self.coder.encode(inp, self.body)
+        res = self.coder.encode(inp, self.body)  # returns with the stream idle
         nb = res.own_hi - res.own_lo
-        h_body[:nb].copy_(self.body[res.own_lo - res.first_byte : res.own_hi - res.first_byte], non_blocking=True)
+        # the link is full duplex: the body goes down on a second stream while the decoder's input comes up
+        with torch.cuda.stream(self._side):
+            h_body[:nb].copy_(self.body[res.own_lo - res.first_byte : res.own_hi - res.first_byte], non_blocking=True)
         self.range.copy_(h_range, non_blocking=True)
         d = self.coder.decode(res.header[4:], res.body_bytes, self.range, self.dec)
         h_text[: d.n_local].copy_(self.dec[: d.n_local], non_blocking=True)
         torch.cuda.synchronize()
         return d.n_local, int(self.plan.n_local + self.range.numel()), int(nb + d.n_local)
+
+
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs NVML reports as local to its GPU, so that its page-locked staging buffers are
+    allocated on that socket: with 8 ranks copying at once the host's memory controllers and the inter-socket link are
+    what the end-to-end number hits first.  Returns a short description (None when the affinity cannot be read/set)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {i for i in range(os.cpu_count()) if (mask[i // 64] >> (i % 64)) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"{len(allowed)} cpus local to gpu {index}"
+    except Exception:
+        return None
 
 
 def verify_one(codec, arm, inp, n, got, kind):
@@ -398,6 +423,7 @@ def run_ours(args, rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the host baseline)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None  # before any pinned allocation: first touch decides the node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -557,6 +583,8 @@ def run_ours(args, rank, world):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "verified_round_trip": verified,
             "decode_check_rounds": stats[-1][4][4], "clocks": clocks.summary(),
         }
+        if numa:
+            line["config"]["numa"] = numa
         if configs is not None:
             line["configs"] = configs
             base = [c for c in configs if c.get("workload") == "text-4G" and "round_trip_gbs" in c]

@@ -41,6 +41,7 @@ struct et_ctx {
     float stage_ms[4] = {0, 0, 0, 0};
     uint32_t last_decode_rounds = 0;  // passes over the chunk entries in the last decode (2 = guesses + one repair round sufficed)
     UnpackTuning tune;                // device properties + et_ctx_set_tuning() knobs
+    UnpackTrie *trie = nullptr;       // host scratch of the dictionary parser (80 KB: not on the stack)
     uint32_t fixed_len = 0;           // the uploaded decoder tables are a complete code whose codes all have this length (0: not so)
     char err[512] = {0};
 };
@@ -55,7 +56,8 @@ constexpr size_t kOffNodes = kOffLut + 2 * kLutSize * 4;            // kMaxTrieN
 constexpr size_t kOffSlots = kOffNodes + kMaxTrieNodes * 4;         // kLutSize x u16 slot of a marker window | sub-tables
 constexpr size_t kOffThresholds = kOffSlots + kLutSize * 2 + (kMaxSubTables << kSubBits) * 2;  // 256 x u32
 constexpr size_t kOffFlags = kOffThresholds + 1024;                 // error flags + total (16 B)
-constexpr size_t kOffHeader = kOffFlags + 64;                       // 4 KiB header staging
+constexpr size_t kOffTableWork = kOffFlags + 64;                    // slot counter + slot windows of launch_build_tables (128 B)
+constexpr size_t kOffHeader = kOffTableWork + 128;                  // 4 KiB header staging
 constexpr size_t kSmallBytes = kOffHeader + 4096;
 constexpr size_t kMaxHeaderBytes = 4096;
 
@@ -264,6 +266,8 @@ extern "C" int et_ctx_create(int device, et_ctx **out) {
     ok = ok && cudaMalloc(reinterpret_cast<void **>(&ctx->d_small), kSmallBytes) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_small), kSmallBytes, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && unpack_init_device(device, &ctx->tune) == cudaSuccess;
+    ctx->trie = new (std::nothrow) UnpackTrie;
+    ok = ok && ctx->trie != nullptr;
     if (const char *v = getenv("ET_LANE_MIN_BYTES")) ctx->tune.lane_min_bytes = atoll(v);  // read once, here
     if (getenv("ET_DEBUG_LANES")) ctx->tune.debug = 1;
     if (!ok) {
@@ -279,6 +283,7 @@ extern "C" void et_ctx_destroy(et_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     unpack_free_device(&ctx->tune);
+    delete ctx->trie;
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_small) cudaFree(ctx->d_small);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -484,30 +489,27 @@ extern "C" int et_pack_shard_dev(et_ctx *ctx, const void *d_in, size_t n, const 
 // ====================================================================== decode
 namespace {
 
-// Build the decoder tables for `dict` and queue their upload on `s`.  validate: ET_FLAG_VALIDATE was passed.
+// The dictionary's trie goes up; the decoder's tables are derived from it on the device (launch_build_tables).
+// validate: ET_FLAG_VALIDATE was passed.
 int upload_unpack_tables(et_ctx *ctx, const et_dictionary &dict, cudaStream_t s, bool validate = false) {
-    UnpackTables *t = new (std::nothrow) UnpackTables;
-    if (!t) return ET_ERR_OUT_OF_MEMORY;
-    int rc = make_unpack_tables(dict, t);
+    UnpackTrie *t = ctx->trie;
+    int rc = make_unpack_trie(dict, t);
     if (rc == ET_OK && validate && !t->prefix_free) rc = ET_ERR_CORRUPT;
     if (rc == ET_OK && validate && !t->complete) rc = ET_ERR_CORRUPT;
     if (rc != ET_OK) {
         const bool why_incomplete = rc == ET_ERR_CORRUPT && validate && t->prefix_free;
-        delete t;
         return fail(ctx, rc, rc == ET_ERR_UNSUPPORTED ? "dictionary code longer than 32 bits"
                              : why_incomplete        ? "dictionary is not a complete code (Kraft sum != 1)"
                                                      : "dictionary is not a prefix code");
     }
-    std::memcpy(ctx->h_small + kOffLut, t->clut, sizeof t->clut);
-    std::memcpy(ctx->h_small + kOffLut + sizeof t->clut, t->wlut, sizeof t->wlut);
-    std::memcpy(ctx->h_small + kOffNodes, t->nodes, (size_t)t->n_nodes * 4);
-    std::memcpy(ctx->h_small + kOffSlots, t->slot_of, sizeof t->slot_of);
-    std::memcpy(ctx->h_small + kOffSlots + sizeof t->slot_of, t->sub, sizeof t->sub);
-    const size_t tbl_bytes = sizeof t->clut + sizeof t->wlut + (size_t)t->n_nodes * 4;
     ctx->fixed_len = (t->complete && t->prefix_free && dict.min_length == dict.max_length) ? dict.max_length : 0u;
-    delete t;
-    ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffLut, ctx->h_small + kOffLut, tbl_bytes, cudaMemcpyHostToDevice, s));
-    ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffSlots, ctx->h_small + kOffSlots, kOffThresholds - kOffSlots, cudaMemcpyHostToDevice, s));
+    std::memcpy(ctx->h_small + kOffNodes, t->nodes, (size_t)t->n_nodes * 4);
+    ET_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + kOffNodes, ctx->h_small + kOffNodes, (size_t)t->n_nodes * 4, cudaMemcpyHostToDevice, s));
+    int launches = 0;
+    ET_CUDA(ctx, launch_build_tables(reinterpret_cast<const uint32_t *>(ctx->d_small + kOffNodes), reinterpret_cast<uint32_t *>(ctx->d_small + kOffLut),
+                                     reinterpret_cast<uint16_t *>(ctx->d_small + kOffSlots), reinterpret_cast<uint32_t *>(ctx->d_small + kOffTableWork), s,
+                                     &launches));
+    ctx->launches += (uint64_t)launches;
     return ET_OK;
 }
 

@@ -235,130 +235,49 @@ int make_pack_tables(const et_codebook &cb, PackTables *t) {
     return ET_OK;
 }
 
-int make_unpack_tables(const et_dictionary &dict, UnpackTables *t) {
-    std::memset(t, 0, sizeof *t);
+// The dictionary as a binary trie - what the device needs: it derives every lookup table from it (build_tables_kernel,
+// lane_tables_kernel) - plus what validation asks about the dictionary.
+// The reference decoder accepts any dictionary: it tries code lengths from the shortest up (decode.zig:175-181), so where
+// one entry is a prefix of another the shorter one always matches first and the longer one can never be reached, and a
+// repeated (length, code) pair overwrites the earlier symbol (decode.zig:123-125).  The same rules here: a longer code that
+// runs into a leaf is dropped, a shorter code that ends on an inner node replaces the subtree, a repeat replaces the leaf;
+// `prefix_free` records whether any of that happened (ET_FLAG_VALIDATE turns it into an error).
+int make_unpack_trie(const et_dictionary &dict, UnpackTrie *t) {
+    t->n_nodes = 0;
+    t->complete = t->prefix_free = false;
     if (dict.n_entries == 0 || dict.n_entries > 256) return ET_ERR_CORRUPT;
     if (dict.max_length > 32) return ET_ERR_UNSUPPORTED;  // reference table is [32]u8 per code (decode.zig:49)
-    t->max_length = dict.max_length;
-    t->min_length = dict.min_length;
-
-    // Binary trie over the dictionary codes.  The reference decoder accepts any dictionary: it tries code
-    // lengths from the shortest up (decode.zig:175-181), so where one entry is a prefix of another the shorter
-    // one always matches first and the longer one can never be reached, and a repeated (length, code) pair
-    // overwrites the earlier symbol (decode.zig:123-125).  The same rules here; `prefix_free` records whether
-    // they were needed (ET_FLAG_VALIDATE turns that into an error).
-    static_assert(kMaxTrieNodes >= 1 + 255 * 32, "trie capacity");
-    uint16_t kid[kMaxTrieNodes][2];
+    uint16_t (*kid)[2] = t->kid;
     uint32_t n_nodes = 1;
     kid[0][0] = kid[0][1] = kChildNone;
     uint64_t kraft = 0;  // in units of 2^-32
     t->prefix_free = true;
-    bool reachable[256];
     for (uint32_t e = 0; e < dict.n_entries; ++e) {
         const unsigned len = dict.length[e];
         if (len == 0) return ET_ERR_CORRUPT;
         kraft += 1ull << (32 - len);
-        reachable[e] = true;
         uint32_t node = 0;
         for (unsigned k = len; k > 0; --k) {
             const unsigned b = (unsigned)((dict.code[e] >> (k - 1)) & 1u);
             uint16_t &slot = kid[node][b];
             if (k == 1) {
-                if (slot != kChildNone) t->prefix_free = false;  // repeated code, or a prefix of longer ones: this entry wins
+                if (slot != kChildNone) t->prefix_free = false;
                 slot = (uint16_t)(kChildLeaf | dict.symbol[e]);
             } else {
                 if (slot == kChildNone) {
                     kid[n_nodes][0] = kid[n_nodes][1] = kChildNone;
                     slot = (uint16_t)n_nodes++;
                 } else if (slot & kChildLeaf) {
-                    t->prefix_free = false;  // a shorter code is a prefix of this one: never reached
-                    reachable[e] = false;
+                    t->prefix_free = false;
                     break;
                 }
                 node = slot;
             }
         }
     }
-    // an entry that lost its place to a later, shorter one (the leaf replaced the subtree it sat in)
-    for (uint32_t e = 0; e < dict.n_entries; ++e) {
-        if (!reachable[e]) continue;
-        uint32_t node = 0;
-        for (unsigned k = dict.length[e]; k > 0 && reachable[e]; --k) {
-            const uint16_t slot = kid[node][(dict.code[e] >> (k - 1)) & 1u];
-            if (k == 1)
-                reachable[e] = slot == (uint16_t)(kChildLeaf | dict.symbol[e]);
-            else if (slot == kChildNone || (slot & kChildLeaf))
-                reachable[e] = false;
-            else
-                node = slot;
-        }
-    }
     t->n_nodes = n_nodes;
     t->complete = kraft == (1ull << 32);
     for (uint32_t i = 0; i < n_nodes; ++i) t->nodes[i] = ((uint32_t)kid[i][1] << 16) | kid[i][0];
-
-    // First-level table.  first[w] = (length << 8 | symbol) of the code that starts window w, filled code by
-    // code (a code of len bits owns 2^(kLutBits-len) windows); 0 = no code of at most kLutBits bits starts here.
-    static_assert(kLutBits <= 16, "window index fits 16 bits");
-    uint16_t first[kLutSize];
-    std::memset(first, 0, sizeof first);
-    for (uint32_t e = 0; e < dict.n_entries; ++e) {
-        const unsigned len = dict.length[e];
-        if (len > (unsigned)kLutBits || !reachable[e]) continue;
-        const uint32_t lo = (uint32_t)(dict.code[e] << (kLutBits - len)), n = 1u << (kLutBits - len);
-        for (uint32_t w = lo; w < lo + n; ++w) first[w] = (uint16_t)((len << 8) | dict.symbol[e]);
-    }
-    // windows that are a proper prefix of longer codes ("markers") and the trie node they stop at
-    uint16_t stuck[kLutSize];
-    for (uint32_t w = 0; w < (uint32_t)kLutSize; ++w) stuck[w] = (uint16_t)kChildNone;
-    for (uint32_t e = 0; e < dict.n_entries; ++e) {
-        const unsigned len = dict.length[e];
-        if (len <= (unsigned)kLutBits || !reachable[e]) continue;
-        const uint32_t w = (uint32_t)(dict.code[e] >> (len - kLutBits));
-        if (stuck[w] != kChildNone) continue;
-        uint32_t node = 0;
-        for (int b = kLutBits - 1; b >= 0; --b) node = kid[node][(w >> b) & 1u];  // an internal node: the code is longer
-        stuck[w] = (uint16_t)node;
-    }
-    // then as many whole codes as fit in the window, one table step per code
-    for (uint32_t idx = 0; idx < (uint32_t)kLutSize; ++idx) {
-        unsigned pos = 0, cnt = 0, len0 = 0, len01 = 0, sym0 = 0, sym1 = 0;
-        for (;;) {
-            const uint16_t f = first[(idx << pos) & (kLutSize - 1)];  // zeros shifted in: a code that ends inside them does not fit
-            const unsigned len = f >> 8;
-            if (len == 0 || pos + len > (unsigned)kLutBits) break;
-            if (cnt == 0) sym0 = f & 0xFFu, len0 = len;
-            if (cnt == 1) sym1 = f & 0xFFu, len01 = pos + len;
-            pos += len;
-            ++cnt;
-            if (pos >= (unsigned)kLutBits) break;
-        }
-        t->slot_of[idx] = kNoSlot;
-        if (cnt == 0) {
-            const uint32_t stuck_node = stuck[idx];
-            t->clut[idx] = kLutMarker | (kLutMarker << 16);
-            t->wlut[idx] = (stuck_node & 0xFFFFu) | (kLutMarker << 16);
-            if (stuck_node != kChildNone && t->n_slots < kMaxSubTables) {  // second level: the next 8 bits
-                t->slot_of[idx] = (uint16_t)t->n_slots++;                  // (filled code by code below; memset left it 0)
-            }
-        } else {
-            const uint32_t all = pos | (cnt << 9), one = len0 | (1u << 9);
-            const uint32_t two = cnt >= 2 ? (len01 | (2u << 9)) : one;
-            t->clut[idx] = all | (one << 16);
-            t->wlut[idx] = sym0 | (sym1 << 8) | (two << 16);
-        }
-    }
-    // second-level tables: a code of kLutBits+1 .. kLutBits+kSubBits bits owns 2^(kLutBits+kSubBits-len) entries of the
-    // table of its first kLutBits bits
-    for (uint32_t e = 0; e < dict.n_entries; ++e) {
-        const unsigned len = dict.length[e];
-        if (len <= (unsigned)kLutBits || len > (unsigned)kLutBits + kSubBits || !reachable[e]) continue;
-        const uint16_t slot = t->slot_of[(uint32_t)(dict.code[e] >> (len - kLutBits))];
-        if (slot == kNoSlot) continue;
-        const unsigned rest = len - kLutBits;  // bits of the code after the window
-        const uint32_t lo = (uint32_t)(dict.code[e] & ((1u << rest) - 1u)) << (kSubBits - rest), n = 1u << (kSubBits - rest);
-        for (uint32_t k = lo; k < lo + n; ++k) t->sub[((uint32_t)slot << kSubBits) + k] = (uint16_t)(dict.symbol[e] | (len << 8));
-    }
     return ET_OK;
 }
 

@@ -24,7 +24,7 @@ constexpr uint32_t kNarrowMaxLen = 32;
 
 int make_pack_tables(const et_codebook &cb, PackTables *t);
 
-// ---------------------------------------------------------------- decoder tables (host -> device)
+// ---------------------------------------------------------------- decoder tables (built on the device from the trie)
 // Two first-level tables indexed by a kLutBits-bit window of the stream.  Entries are
 // pre-packed "adds" for a walk state that keeps the bit position in bits 0-8 and a symbol
 // count (or output address) in bits 9+:   add = bits_consumed | symbols << 9.
@@ -51,21 +51,13 @@ constexpr uint32_t kSubBits = 8;
 constexpr uint32_t kMaxSubTables = 16;
 constexpr uint16_t kNoSlot = 0xFFFFu;
 
-struct UnpackTables {
-    uint32_t clut[kLutSize];
-    uint32_t wlut[kLutSize];
+struct UnpackTrie {
     uint32_t nodes[kMaxTrieNodes];
-    uint16_t slot_of[kLutSize];                      // marker window -> slot, kNoSlot otherwise
-    uint16_t sub[kMaxSubTables << kSubBits];
-    uint32_t n_slots;
+    uint16_t kid[kMaxTrieNodes][2];  // scratch of the builder
     uint32_t n_nodes;
-    uint32_t max_length;
-    uint32_t min_length;
-    bool complete;     // every window decodes (Kraft sum == 1)
-    bool prefix_free;  // no entry is a prefix (or a repeat) of another
+    bool complete, prefix_free;
 };
-
-int make_unpack_tables(const et_dictionary &dict, UnpackTables *t);
+int make_unpack_trie(const et_dictionary &dict, UnpackTrie *t);
 
 // "{d} B" / "{d:.2} KB" ... of utils.zig:3-13 (byte_count is an f32 there).
 void format_file_size(char *buf, size_t cap, double byte_count);

@@ -91,7 +91,7 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes);
 // by the first chunk, [28] exit of the last chunk (u32 bits).  Writes min(total, max_symbols)
 // bytes to d_out.  Blocks on the stream between check rounds; on return the stream is idle and
 // h_hdr (pinned host memory, 64 bytes) holds a copy of the first 32 bytes of the scratch header.
-// d_slots: UnpackTables::slot_of followed by UnpackTables::sub (second-level tables of the lane-interleaved decoder).
+// d_slots: slot of every marker window (kLutSize x u16) followed by the second-level tables (launch_build_tables).
 // *rounds_out = passes over the chunk entries it took (2 = the guesses plus one repair round sufficed).
 // fixed_len: the dictionary is a complete code whose codes all have this many bits (0: it is not) — such a
 // stream never re-synchronises, but every chunk's entry follows from the first one in closed form.
@@ -102,6 +102,10 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
                           const uint32_t *d_nodes, const uint16_t *d_slots, uint8_t *d_out, uint64_t max_symbols, void *scratch_base,
                           uint8_t *h_hdr, cudaStream_t stream, const UnpackTuning &tune, uint32_t fixed_len, uint32_t transfer_states,
                           int *launches, uint32_t *rounds_out);
+
+// The decoder's first-level tables (et_internal.h) from the uploaded trie, on the device.
+cudaError_t launch_build_tables(const uint32_t *d_nodes, uint32_t *d_clut, uint16_t *d_slots, uint32_t *d_work, cudaStream_t stream,
+                                int *launches);
 
 // ---------------------------------------------------------------- synthetic input generator
 cudaError_t launch_synth(uint8_t *d_out, size_t n, uint64_t seed, uint64_t first_index, const uint32_t *d_thresholds,

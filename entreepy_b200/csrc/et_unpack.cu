@@ -69,6 +69,9 @@ struct DecArgs {
     unsigned long long *group_prefix;  // [ceil(regions / 1024)] lane-interleaved decoder: scan of the group sums
     uint32_t *work;               // [regions] lane-interleaved decoder: regions in which an entry has to be repaired
     uint32_t *work_count;         // [1]
+    uint32_t *edge;               // [regions] lane-interleaved decoder: entry of the region's first chunk | exit of its last << 16
+    uint8_t *self_listed;         // [regions] ... the count walk put the region on the repair list itself
+    uint32_t *rsum;               // [regions] ... symbols of the region
     uint32_t *error_flags;
     unsigned long long *total;
     uint32_t *entry_exit;
@@ -744,6 +747,73 @@ __global__ void __launch_bounds__(kChunkThreads, 5) chunk_write_kernel(const Dec
     if (bad) atomicOr(a.error_flags, kErrInvalidCode);
 }
 
+// ------------------------------------------------------------------ first-level tables from the trie, on the device
+// The host parses the dictionary into a trie (a few hundred nodes, microseconds) and uploads only that; the lookup tables
+// every decoder kernel reads (clut, wlut, marker slots, second-level tables: layouts in et_internal.h) are derived from
+// it here, one thread per 12-bit window - without 80 KB of host table building and upload in front of every decode.
+__global__ void __launch_bounds__(256) build_tables_kernel(const uint32_t *__restrict__ nodes, uint32_t *__restrict__ clut,
+                                                           uint32_t *__restrict__ wlut, uint16_t *__restrict__ slots,
+                                                           uint32_t *__restrict__ slot_count, uint32_t *__restrict__ slot_window) {
+    const uint32_t w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= (uint32_t)kLutSize) return;
+    uint32_t node = 0, pos = 0, cnt = 0, len0 = 0, len01 = 0, sym0 = 0, sym1 = 0;
+    bool dead = false;  // ran into a bit pattern that is no code
+    for (uint32_t b = 0; b < (uint32_t)kLutBits; ++b) {
+        const uint32_t child = (__ldg(nodes + node) >> (16 * ((w >> (kLutBits - 1 - b)) & 1u))) & 0xFFFFu;
+        if (child == kChildNone) {
+            dead = true;
+            break;
+        }
+        if (child & kChildLeaf) {
+            if (cnt == 0) sym0 = child & 0xFFu, len0 = b + 1;
+            if (cnt == 1) sym1 = child & 0xFFu, len01 = b + 1;
+            ++cnt;
+            pos = b + 1;
+            node = 0;
+        } else {
+            node = child;
+        }
+    }
+    uint16_t slot = kNoSlot;
+    if (cnt == 0) {
+        const uint32_t stuck = dead ? kChildNone : node;  // the trie node the window's bits lead to: the code is longer
+        clut[w] = kLutMarker | (kLutMarker << 16);
+        wlut[w] = (stuck & 0xFFFFu) | (kLutMarker << 16);
+        if (stuck != kChildNone) {  // second level: the next 8 bits (the first kMaxSubTables marker windows to ask get one)
+            const uint32_t k = atomicAdd(slot_count, 1u);
+            if (k < kMaxSubTables) {
+                slot = (uint16_t)k;
+                slot_window[k] = w | (stuck << 16);
+            }
+        }
+    } else {
+        const uint32_t all = pos | (cnt << 9), one = len0 | (1u << 9);
+        const uint32_t two = cnt >= 2 ? (len01 | (2u << 9)) : one;
+        clut[w] = all | (one << 16);
+        wlut[w] = sym0 | (sym1 << 8) | (two << 16);
+    }
+    slots[w] = slot;
+}
+// sub[slot][next 8 bits] = symbol | length << 8 for codes of 13..20 bits behind a marker window, 0 otherwise.
+__global__ void __launch_bounds__(256) build_sub_tables_kernel(const uint32_t *__restrict__ nodes, uint16_t *__restrict__ slots,
+                                                               const uint32_t *__restrict__ slot_count, const uint32_t *__restrict__ slot_window) {
+    const uint32_t slot = blockIdx.x, x = threadIdx.x;  // one block per slot, one thread per 8-bit continuation
+    uint16_t entry = 0;
+    if (slot < min(*slot_count, kMaxSubTables)) {
+        uint32_t node = slot_window[slot] >> 16;
+        for (uint32_t b = 0; b < kSubBits; ++b) {
+            const uint32_t child = (__ldg(nodes + node) >> (16 * ((x >> (kSubBits - 1 - b)) & 1u))) & 0xFFFFu;
+            if (child == kChildNone) break;
+            if (child & kChildLeaf) {
+                entry = (uint16_t)((child & 0xFFu) | ((kLutBits + b + 1) << 8));
+                break;
+            }
+            node = child;
+        }
+    }
+    slots[kLutSize + (slot << kSubBits) + x] = entry;
+}
+
 #include "et_lanes.inc"
 
 uint64_t chunk_count(const UnpackGeometry &g, uint32_t chunk_bytes) {
@@ -770,6 +840,18 @@ cudaError_t unpack_init_device(int device, UnpackTuning *tune) {
 void unpack_free_device(UnpackTuning *tune) {
     if (tune->d_lane_tables) cudaFree(tune->d_lane_tables);
     tune->d_lane_tables = nullptr;
+}
+
+// d_nodes holds the trie (uploaded); builds clut | wlut (contiguous: d_clut, d_clut + kLutSize) and the slot / second-level
+// tables.  d_work: 2 + kMaxSubTables words of device scratch.
+cudaError_t launch_build_tables(const uint32_t *d_nodes, uint32_t *d_clut, uint16_t *d_slots, uint32_t *d_work, cudaStream_t stream,
+                                int *launches) {
+    cudaError_t err = cudaMemsetAsync(d_work, 0, 4, stream);
+    if (err != cudaSuccess) return err;
+    build_tables_kernel<<<kLutSize / 256, 256, 0, stream>>>(d_nodes, d_clut, d_clut + kLutSize, d_slots, d_work, d_work + 2);
+    build_sub_tables_kernel<<<kMaxSubTables, 1u << kSubBits, 0, stream>>>(d_nodes, d_slots, d_work, d_work + 2);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
 }
 
 UnpackGeometry unpack_geometry(const void *d_body, size_t body_bytes) {
@@ -839,7 +921,7 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t ng = (nb + kGroupRegions - 1) / kGroupRegions;
     // exit (u8) and symbols (u16) per (chunk, entry); a map per segment of chunks and per block of segments
     const size_t transfer = chunk_bytes == kLaneBytes ? 0 : (size_t)n * kMaxStates * 3 + 64 + ((size_t)n / kSegChunks + 2 * kSegThreads + 64) * 8;
-    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 4) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * 4 + 64 + transfer;
+    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 4) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * (4 + 4 + 4 + 1) + 320 + transfer;
 }
 
 // Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
@@ -876,9 +958,13 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
         if (launches) *launches += 2;
         return cudaSuccess;
     };
+    if ((err = cudaMemsetAsync(a.work_count, 0, 4, stream)) != cudaSuccess) return err;
     region_sync_kernel<<<sync_grid, sync_warps * 32, sync_smem, stream>>>(a, n_regions, 0, sync_warps);
-    if (launches) *launches += 1;
-    if ((err = repair(1)) != cudaSuccess) return err;
+    // first repair round: the count walk listed the regions whose chunks disagree, edge_check adds those whose first
+    // chunk does not start where the region before ended
+    edge_check_kernel<<<(n_regions + 255) / 256, 256, 0, stream>>>(a, n_regions);
+    region_sync_kernel<<<sync_grid, sync_warps * 32, sync_smem, stream>>>(a, n_regions, 1, sync_warps);
+    if (launches) *launches += 3;
     if ((err = cudaMemsetAsync(a.changed, 0, 8, stream)) != cudaSuccess) return err;  // changed and max_sum
     uint32_t rounds = 2;
     for (;;) {
@@ -993,7 +1079,10 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 12 + 63) & ~(size_t)63));
     a.work = reinterpret_cast<uint32_t *>(a.group_prefix + (nb + 1023) / 1024 + 1);
     a.work_count = reinterpret_cast<uint32_t *>(p + 32);
-    a.tr_exit = reinterpret_cast<uint8_t *>(a.work) + (((size_t)nb * 4 + 64 + 63) & ~(size_t)63);
+    a.edge = a.work + nb + 8;
+    a.rsum = a.edge + nb + 8;
+    a.self_listed = reinterpret_cast<uint8_t *>(a.rsum + nb + 8);
+    a.tr_exit = reinterpret_cast<uint8_t *>(a.work) + (((size_t)nb * 13 + 256 + 63) & ~(size_t)63);
     a.tr_cnt = reinterpret_cast<uint16_t *>(a.tr_exit + (size_t)n * kMaxStates);
     a.out = d_out;
     a.max_symbols = max_symbols;
