@@ -408,16 +408,24 @@ __device__ __forceinline__ void region_copy_out(const PackArgs &a, uint32_t r, c
             if (k0 >= s_lo && k0 + 16 <= s_hi) {
                 st_stream_v4(gbase + k0, v);
             } else {
-                // a block at the ragged start or end of the region: bytewise, through a small buffer
-                uint4 *tmp = reinterpret_cast<uint4 *>(edge + (c == 0 ? 0 : 16));
-                *tmp = v;
-                const uint8_t *tb = reinterpret_cast<const uint8_t *>(tmp);
-                const uint32_t lo_k = max(k0, s_lo), hi_k = min(k0 + 16u, s_hi);
-                for (uint32_t kk = lo_k; kk < hi_k; ++kk) gbase[kk] = tb[kk - k0];
-                if (has_head && s_head >= k0 && s_head < k0 + 16u) a.seam_head[r] = tb[s_head - k0];
-                if (has_tail && s_tail >= k0 && s_tail < k0 + 16u) a.seam_tail[r] = tb[s_tail - k0];
+                // a block at the ragged start (slot 0) or end (slot 1) of the region: parked, the warp stores its bytes below
+                *reinterpret_cast<uint4 *>(edge + (c == 0 ? 0 : 16)) = v;
             }
         }
+        // The two ragged blocks, one byte per lane (lanes 0-15: the first block, 16-31: the last one): a single lane
+        // walking their bytes one at a time cost the warp ~200 instructions per region with 31 lanes idle.
+        __syncwarp();
+        if (n_chunks) {
+            const uint32_t blk = lane < 16 ? 0u : n_chunks - 1u, k0 = blk * 16u, k = k0 + (lane & 15u);
+            const bool ragged = !(k0 >= s_lo && k0 + 16u <= s_hi) && (lane < 16 || n_chunks > 1);
+            if (ragged) {
+                const uint32_t byte = edge[(lane < 16 ? 0u : 16u) + (lane & 15u)];
+                if (k >= s_lo && k < s_hi) gbase[k] = (uint8_t)byte;
+                if (has_head && k == s_head) a.seam_head[r] = (uint8_t)byte;
+                if (has_tail && k == s_tail) a.seam_tail[r] = (uint8_t)byte;
+            }
+        }
+        __syncwarp();  // the slots are free again
     }
 }
 
