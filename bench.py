@@ -540,7 +540,7 @@ def run_ours(args, rank, world):
                 if traffic is not None else None,
                 "algorithmic_bytes": alg_bytes, "ms": ms, "peak_source": peak_src}
 
-    roofs = [roof("pack (run_bits_kernel + pack_runs_kernel)", ["run_bits_kernel", "pack_runs_kernel"], n + c_local, pack_ms),
+    roofs = [roof("pack (region_bits_kernel + pack_runs_kernel)", ["region_bits_kernel", "pack_runs_kernel"], n + c_local, pack_ms),
              roof("unpack (region_sync_kernel + region_write_kernel)", ["region_sync_kernel", "region_write_kernel"],
                   c_dec + got, unpack_ms)]
     if world == 1:

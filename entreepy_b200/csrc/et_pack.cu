@@ -3,10 +3,10 @@
 // Codes of at most 32 bits (every dictionary the reference emits faithfully) take the lane-run
 // path: two streaming passes with warps as the unit of work, nothing waits at a block-wide
 // barrier.
-//   pass A  run_bits_kernel   bits of every run of 64 consecutive symbols, of the regions
-//                             (32 runs = 2048 symbols) before each region inside its group of
-//                             regions, and of every group;
-//   scan    group_scan_kernel one block: bits before every group;
+//   pass A  region_bits_kernel  bits of every run of 64 consecutive symbols and of every region (32 runs =
+//                               2048 symbols), a warp per region;
+//   scan    region_prefix_kernel + group_scan_kernel: bits before each region inside its group of 1024, bits
+//                               before every group;
 //   pass B  pack_runs_kernel  persistent warps, one region at a time.  A lane owns one run: its
 //                             bit offset inside the region comes from a warp scan of the run
 //                             totals; per symbol one conflict-free 64-bit shared load of
@@ -115,21 +115,6 @@ constexpr int kTableLanes = 16;
 constexpr int kTableBytes = 256 * kTableLanes * 8;                    // 32 KiB
 constexpr int kStageGuard = 4;                                        // zero words in front of the image
 
-// 16 input bytes of thread `tid` of `tile`, and which of them exist (edge tiles only).
-__device__ __forceinline__ uint4 load_symbols(const PackArgs &a, uint32_t tile, uint32_t tid, bool interior,
-                                              uint32_t *valid) {
-    const uint64_t v0 = (uint64_t)tile * kPackTileSyms + (uint64_t)tid * kPackItems;  // virtual byte index
-    *valid = 0xffffu;
-    if (interior) return ld_stream_v4(a.in_aligned + v0);
-    const long long lo = (long long)a.misalign - (long long)v0, hi = (long long)a.v_end - (long long)v0;
-    const int l = (int)max(lo, 0ll), h = (int)min(hi, 16ll);
-    if (h <= 0 || l >= 16) {
-        *valid = 0;
-        return make_uint4(0, 0, 0, 0);
-    }
-    *valid = (0xffffu >> (16 - h)) & (0xffffu << l);
-    return ld_partial_v4(a.in_aligned + v0, l, h);
-}
 // ---- scan: bits before each group (one block; groups are sized so that there are at most a few thousand).
 __global__ void __launch_bounds__(1024) group_scan_kernel(const PackArgs a, uint32_t n_groups) {
     __shared__ unsigned long long part[1024];
@@ -158,7 +143,7 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(const PackArgs a, uint
 // The same two passes with warps instead of CTAs as the unit, so that nothing waits at a
 // block-wide barrier and the per-tile overhead (block scan, three barriers, image zeroing by the
 // whole CTA) is gone:
-//   pass A  run_bits_kernel: one streaming pass; bits of every RUN of 64 consecutive symbols
+//   pass A  region_bits_kernel: one streaming pass; bits of every RUN of 64 consecutive symbols
 //           (u16), of every region of 32 runs before it inside its group, of every group;
 //   scan    group_scan_kernel (one block);
 //   pass B  pack_runs_kernel: persistent warps.  A lane owns one run: four 16-byte loads, its
@@ -193,84 +178,75 @@ __device__ __forceinline__ void push_acc(BitAcc &b, uint32_t code, uint32_t len)
     b.pos = p2;
 }
 
-// Pass A.  A CTA iteration covers a slab of 4096 symbols = two regions (warps 0-3 / 4-7); thread t holds
-// 16 symbols, four neighbouring threads make a run.
-__global__ void __launch_bounds__(kPackThreads) run_bits_kernel(const PackArgs a) {
+// Pass A, a warp per region: four coalesced 16-byte loads per lane, a run's bit count is the sum over the four lanes that
+// hold it (two shuffles), and nothing in the kernel waits for anything - no barrier, no running total carried by one
+// thread (round 1's slab form, 4096 symbols per CTA step with the group's running total kept
+// by thread 0, spent a third of its issue slots on those: 288 us per GiB against ~190 us here).  It writes the
+// run totals and every region's total; region_prefix_kernel turns the totals into prefixes inside groups of 1024.
+__global__ void __launch_bounds__(kPackThreads) region_bits_kernel(const PackArgs a) {
     __shared__ uint32_t len_sh[256 * 32];  // [sym][lane]: a warp-wide lookup never has a bank conflict
-    __shared__ uint32_t warp_sum[2][4 * kWarps];
     for (int i = threadIdx.x; i < 256 * 32; i += kPackThreads) len_sh[i] = static_cast<const uint2 *>(a.tables)[i >> 5].y;
     __syncthreads();
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     const uint8_t *len_lane = reinterpret_cast<const uint8_t *>(len_sh) + lane * 4;
-    const uint32_t n_slabs = (a.n_regions + 1) / 2, group_slabs = a.group_tiles / 2;
-    const uint32_t s_lo = blockIdx.x * group_slabs, s_hi = min(s_lo + group_slabs, n_slabs);
-    const uint32_t slab_int_lo = (a.interior_lo + 1) / 2, slab_int_hi = a.interior_hi / 2;  // slabs wholly inside the input
-    uint32_t run = 0;  // bits of the group so far (kept by warp 0)
-    constexpr int kBatch = 4;  // slabs per iteration: four independent 16-byte loads in flight per thread
-    for (uint32_t s0 = s_lo; s0 < s_hi; s0 += kBatch) {
-        uint4 raw[kBatch];
-        uint32_t valid[kBatch];
-        bool interior[kBatch];
+    const uint32_t stride = gridDim.x * kWarps;
+    for (uint32_t r = blockIdx.x * kWarps + (threadIdx.x >> 5); r < a.n_regions; r += stride) {
+        if (region_is_interior(a, r)) {
+            // coalesced: load i of lane L is vector 32 i + L of the region, i.e. a quarter of run 8 i + L / 4 (a lane loading
+            // its own run, 64 bytes apart from its neighbour's, fetches every 32-byte sector twice from L2: measured 2.09 GB
+            // of L2 traffic per GiB and an L2-bound kernel)
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.in_aligned + (uint64_t)r * kRegionSyms) + lane;
+            const uint4 v[4] = {ld_stream_v4(src), ld_stream_v4(src + 32), ld_stream_v4(src + 64), ld_stream_v4(src + 96)};
+            uint32_t total = 0;
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-            const uint32_t slab = s0 + b;
-            interior[b] = slab < s_hi && slab >= slab_int_lo && slab < slab_int_hi;
-            valid[b] = 0xffffu;
-            if (interior[b])
-                raw[b] = ld_stream_v4(a.in_aligned + (uint64_t)slab * kPackTileSyms + (uint64_t)tid * kPackItems);
-            else if (slab < s_hi)
-                raw[b] = load_symbols(a, slab, tid, false, &valid[b]);
-            else {
-                raw[b] = make_uint4(0, 0, 0, 0);
-                valid[b] = 0;
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                uint32_t bits = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    bits += *reinterpret_cast<const uint32_t *>(len_lane + ((w[q] << 7) & 0x7f80u)) +
+                            *reinterpret_cast<const uint32_t *>(len_lane + ((w[q] >> 1) & 0x7f80u)) +
+                            *reinterpret_cast<const uint32_t *>(len_lane + ((w[q] >> 9) & 0x7f80u)) +
+                            *reinterpret_cast<const uint32_t *>(len_lane + ((w[q] >> 17) & 0x7f80u));
+                bits += __shfl_xor_sync(0xffffffffu, bits, 1);
+                bits += __shfl_xor_sync(0xffffffffu, bits, 2);  // the run's bits, in its four lanes
+                if ((lane & 3u) == 0) a.run_bits[(size_t)r * 32 + 8 * i + (lane >> 2)] = (uint16_t)bits;
+                total += (lane & 3u) == 0 ? bits : 0u;
             }
+            total = __reduce_add_sync(0xffffffffu, total);
+            if (lane == 0) a.tile_bits[r] = total;
+            continue;
         }
-        uint32_t bits[kBatch];
-#pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-            const uint32_t rw[4] = {raw[b].x, raw[b].y, raw[b].z, raw[b].w};
-            bits[b] = 0;
-            if (interior[b]) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t w = rw[q];  // byte -> byte offset sym*128 into this lane's column
-                    bits[b] += *reinterpret_cast<const uint32_t *>(len_lane + ((w << 7) & 0x7f80u)) +
-                               *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 1) & 0x7f80u)) +
-                               *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 9) & 0x7f80u)) +
-                               *reinterpret_cast<const uint32_t *>(len_lane + ((w >> 17) & 0x7f80u));
-                }
-            } else if (valid[b]) {
-#pragma unroll
-                for (int i = 0; i < kPackItems; ++i) {
-                    const uint32_t len = len_sh[((rw[i >> 2] >> (8 * (i & 3))) & 0xffu) * 32];
-                    bits[b] += ((valid[b] >> i) & 1u) ? len : 0u;
-                }
-            }
-            bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], 1);
-            bits[b] += __shfl_xor_sync(0xffffffffu, bits[b], 2);
-            if ((lane & 3u) == 0 && s0 + b < s_hi) a.run_bits[(size_t)(s0 + b) * 64 + (tid >> 2)] = (uint16_t)bits[b];
-            bits[b] = __reduce_add_sync(0xffffffffu, (lane & 3u) == 0 ? bits[b] : 0u);  // one REDUX instead of three shuffles
+        uint32_t bits = 0;
+        {  // ragged ends of the input: a lane takes its own run, only the symbols that exist
+            const uint64_t v0 = (uint64_t)r * kRegionSyms + (uint64_t)lane * kRunSyms;
+            for (uint32_t i = 0; i < (uint32_t)kRunSyms; ++i)
+                if (v0 + i >= a.misalign && v0 + i < a.v_end) bits += len_sh[(uint32_t)a.in_aligned[v0 + i] * 32];
         }
-        uint32_t *ws = warp_sum[((s0 - s_lo) / kBatch) & 1];  // double-buffered: one barrier per batch
-        if (lane == 0) {
-#pragma unroll
-            for (int b = 0; b < kBatch; ++b) ws[b * kWarps + warp] = bits[b];
-        }
-        __syncthreads();
-        if (warp == 0) {  // only the thread that writes the prefixes needs the running total
-#pragma unroll
-            for (int b = 0; b < kBatch; ++b) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {  // the two regions of the slab
-                    const uint32_t r = 2 * (s0 + b) + h;
-                    if (tid == 0 && s0 + b < s_hi && r < a.n_regions) a.tile_bits[r] = run;
-#pragma unroll
-                    for (int q = 0; q < kWarps / 2; ++q) run += ws[b * kWarps + h * (kWarps / 2) + q];
-                }
-            }
-        }
+        a.run_bits[(size_t)r * 32 + lane] = (uint16_t)bits;
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bits);
+        if (lane == 0) a.tile_bits[r] = total;
     }
-    if (tid == 0) a.group_prefix[blockIdx.x] = run;  // group total; group_scan_kernel turns it into a prefix
+}
+// tile_bits[r]: the region's bits -> bits of the regions before it inside its group of kPrefixGroup; group_prefix[g]: the
+// group's bits (group_scan_kernel makes prefixes of those).
+constexpr uint32_t kPrefixGroup = 1024;
+__global__ void __launch_bounds__(kPrefixGroup) region_prefix_kernel(const PackArgs a) {
+    __shared__ uint32_t warp_sum[32];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t r = blockIdx.x * kPrefixGroup + t;
+    const uint32_t v = r < a.n_regions ? a.tile_bits[r] : 0u;
+    const uint32_t incl = warp_inclusive_scan(v, lane);
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (uint32_t w = 0; w < 32; ++w) {
+        const uint32_t s = warp_sum[w];
+        if (w < warp) before += s;
+        total += s;
+    }
+    if (r < a.n_regions) a.tile_bits[r] = before + incl - v;
+    if (t == 0) a.group_prefix[blockIdx.x] = total;
 }
 
 // Four vectors of a lane's run and which of the 64 symbols exist (ragged ends of the input only).
@@ -818,14 +794,6 @@ PackGeometry pack_geometry(const void *d_in, size_t n) {
     return g;
 }
 
-// Tiles per group: groups are the CTAs of pass A and the entries of the one-block scan, so
-// there should be a few per SM but no more than a few thousand.
-static uint32_t pack_group_tiles(uint32_t num_tiles) {
-    uint32_t gt = 8;
-    while (gt < 256 && num_tiles / gt > 2048) gt <<= 1;
-    while (num_tiles / gt > 8192) gt <<= 1;
-    return gt;
-}
 // The lane-run path cuts the input into regions of 2048 symbols (two per tile) and keeps a u16 per run of 64.
 size_t pack_scratch_bytes(uint32_t num_tiles) {
     // [ticket + pad : 16][tile_state : 8*T][group_prefix : 8*G][tile_bits : 4*T][seam_head : T][seam_tail : T][run_bits : 64*T]
@@ -933,11 +901,18 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
                 return cudaGetLastError();
             }
         }
-        a.group_tiles = pack_group_tiles(n_regions);
-        if (a.group_tiles < 2) a.group_tiles = 2;
-        for (a.group_shift = 0; (1u << a.group_shift) < a.group_tiles; ++a.group_shift) {}
-        const uint32_t groups = (n_regions + a.group_tiles - 1) / a.group_tiles;
-        run_bits_kernel<<<groups, kPackThreads, 0, stream>>>(a);
+        // pass A: run and region totals (a warp per region), prefixes inside groups of 1024 regions, prefixes of the groups
+        // (a region holds at most 2048 x 32 bits, a group 2^26: the prefix inside a group fits 32 bits)
+        a.group_tiles = kPrefixGroup;
+        a.group_shift = 10;
+        const uint32_t groups = (n_regions + kPrefixGroup - 1) / kPrefixGroup;
+        {
+            unsigned pa_grid = (unsigned)num_sms * 6u;  // 6 CTAs of 8 warps per SM: the 32 KB table and 48 registers allow it
+            const unsigned need = (n_regions + kWarps - 1) / kWarps;
+            if (pa_grid > need) pa_grid = need;
+            region_bits_kernel<<<pa_grid, kPackThreads, 0, stream>>>(a);
+        }
+        region_prefix_kernel<<<groups, kPrefixGroup, 0, stream>>>(a);
         group_scan_kernel<<<1, 1024, 0, stream>>>(a, groups);
         const int smem = kTableBytes + kRunWarps * (int)a.image_words * 4 + kRunWarps * 32;
         err = cudaFuncSetAttribute(pack_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -949,7 +924,7 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         const unsigned need = (n_regions + kRunWarps - 1) / kRunWarps;
         if (grid > need) grid = need;
         pack_runs_kernel<<<grid, kRunWarps * 32, smem, stream>>>(a);
-        if (launches) *launches += 3;
+        if (launches) *launches += 4;
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         seam_fixup_kernel<<<(n_regions + 255) / 256, 256, 0, stream>>>(a.tile_state, a.seam_head, a.seam_tail, n_regions,
