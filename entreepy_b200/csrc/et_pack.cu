@@ -424,11 +424,37 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
     uint32_t r = blockIdx.x * kRunWarps + warp;
     if (r >= a.n_regions) return;
 
+    const uint32_t stage_run_s = (uint32_t)__cvta_generic_to_shared(stage + kStageGuard);
     for (;;) {
         const bool interior = region_is_interior(a, r);
         uint4 raw[4];
-        unsigned long long valid;
-        load_run(a, r, lane, interior, raw, &valid);
+        unsigned long long valid = ~0ull;
+        if (interior) {
+            // The region's 2 KiB come in with coalesced cp.async (L2 -> shared memory, no registers) into the warp's bit
+            // image, which is idle until the packing starts; a lane then reads its own run - 64 bytes - from there.  (A
+            // lane loading its run straight from global memory shares every 32-byte sector with its neighbour and pulls
+            // it from L2 twice.)  The 16-byte pieces of a run are stored XOR-swizzled so that neither the cp.async
+            // writes nor the four 16-byte reads of a lane meet in a bank.
+            const uint8_t *src = a.in_aligned + (uint64_t)r * kRegionSyms;
+#pragma unroll
+            for (uint32_t i = 0; i < 4; ++i) {
+                const uint32_t v = 32u * i + lane, chunk = (v & ~3u) | ((v & 3u) ^ ((v >> 3) & 3u));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_run_s + 16u * chunk), "l"(src + 16u * v) : "memory");
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+                const uint32_t chunk = 4u * lane + (j ^ ((lane >> 1) & 3u));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(raw[j].x), "=r"(raw[j].y), "=r"(raw[j].z), "=r"(raw[j].w)
+                             : "r"(stage_run_s + 16u * chunk)
+                             : "memory");
+            }
+            __syncwarp();  // every lane holds its run: the image may be written
+        } else {
+            load_run(a, r, lane, false, raw, &valid);
+        }
         const uint32_t my_bits = a.run_bits[(size_t)r * 32 + lane];
         const unsigned long long bit_begin = a.group_prefix[r >> a.group_shift] + a.tile_bits[r];
         const uint32_t r_next = r + stride;
@@ -873,6 +899,7 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         a.interior_hi = (uint32_t)(g.v_end / kRegionSyms);
         if (a.interior_hi < a.interior_lo) a.interior_hi = a.interior_lo;
         a.image_words = (uint32_t)(kStageGuard + (kRegionSyms * max_len + 31) / 32 + 16 + 3) & ~3u;
+        if (a.image_words < kStageGuard + kRegionSyms / 4) a.image_words = kStageGuard + kRegionSyms / 4;  // the image also stages the region's text
         if (single_pass) {
             // single pass: tiles of `warps` regions, look-back descriptors where the two-pass path keeps its run totals
             const uint32_t priv_stride = (2u * max_len + 1u) | 1u;  // words of a lane's private string (64 codes), odd: lanes never share a bank at equal depth
