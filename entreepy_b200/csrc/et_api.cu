@@ -318,6 +318,7 @@ extern "C" int et_ctx_set_tuning(et_ctx *ctx, int key, long long value) {
         case ET_TUNE_LANE_MIN_BYTES: ctx->tune.lane_min_bytes = value; return ET_OK;
         case ET_TUNE_DEBUG: ctx->tune.debug = value != 0; return ET_OK;
         case ET_TUNE_SYNC_WARPS: ctx->tune.sync_warps = (int)value; return ET_OK;
+        case ET_TUNE_WRITE_WARPS: ctx->tune.write_warps = (int)value; return ET_OK;
         case ET_TUNE_NO_TRANSFER: ctx->tune.no_transfer = value != 0; return ET_OK;
         case ET_TUNE_PACK_SINGLE_PASS: ctx->tune.pack_single_pass = value != 0; return ET_OK;
     }

@@ -77,6 +77,7 @@ struct UnpackTuning {
     int max_smem = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int num_sms = 0;
     int sync_warps = 0;             // > 0: warps per CTA of the count walk (default: as many as fit)
+    int write_warps = 0;            // > 0: warps per CTA of the write walk (default: as many as fit)
     int no_transfer = 0;            // non-zero: slowly synchronising codes take the repair rounds instead of transfer functions
     int pack_single_pass = 0;       // non-zero: the encoder packs in ONE pass with a decoupled look-back (measured slower, see et_pack.cu)
     void *d_lane_tables = nullptr;  // device-built tables of the lane-interleaved decoder

@@ -974,7 +974,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
         region_apply_kernel<<<n_groups, 1024, 0, stream>>>(a, n_regions);
         const uint32_t write_blocks = (n_regions + 15u) / 16u;
         region_write_kernel<<<write_blocks < (uint32_t)num_sms ? write_blocks : (uint32_t)num_sms, 512, max_smem, stream>>>(
-            a, n_regions, (uint32_t)max_smem);
+            a, n_regions, (uint32_t)max_smem, tune.write_warps > 0 ? (uint32_t)tune.write_warps : 16u);
         if (launches) *launches += 4;
         // one look at the scratch header: error flags, symbols found, "an entry was wrong", entry and exit of the shard
         if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;

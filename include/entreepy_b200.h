@@ -119,6 +119,7 @@ ET_API uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx);
 #define ET_TUNE_SYNC_WARPS 3     /* warps per CTA of the decoder's count walk; 0 = as many as fit */
 #define ET_TUNE_NO_TRANSFER 5     /* non-zero: slowly synchronising codes are decoded with repair rounds (round 1's way) instead of
                                      the scan of per-chunk transfer functions */
+#define ET_TUNE_WRITE_WARPS 6     /* warps per CTA of the decoder's write walk; 0 = as many as fit */
 #define ET_TUNE_PACK_SINGLE_PASS 4 /* non-zero: the encoder packs in one pass over the text (decoupled look-back over tile
                                      descriptors) instead of two (run totals, then pack); measured slower on B200, kept selectable */
 ET_API int et_ctx_set_tuning(et_ctx *ctx, int key, long long value);

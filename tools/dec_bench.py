@@ -27,6 +27,10 @@ else:
     w = [0] + [1] * 255
 thr = synth.thresholds_from_weights(w)
 c = et.Codec(0)
+if os.environ.get("ET_WRITE_WARPS"):
+    c.set_tuning(et._abi.TUNE_WRITE_WARPS, int(os.environ["ET_WRITE_WARPS"]))
+if os.environ.get("ET_SYNC_WARPS"):
+    c.set_tuning(et._abi.TUNE_SYNC_WARPS, int(os.environ["ET_SYNC_WARPS"]))
 if os.environ.get("ET_PACK_SINGLE_PASS"):
     c.set_tuning(et._abi.TUNE_PACK_SINGLE_PASS, 1)
 dev = torch.empty(n, dtype=torch.uint8, device="cuda")
