@@ -62,7 +62,7 @@ struct DecArgs {
     uint16_t *start_off;          // [n] first codeword of the chunk, bits past the chunk's first bit
     uint16_t *exit_off;           // [n] first codeword boundary at or after the chunk's end, bits past that end
     uint32_t *count;              // [n] symbols that begin inside the chunk
-    uint32_t *mid;                // [n] lane-interleaved decoder: entry of the chunk's second part | symbols of the first << 16
+    uint64_t *mid;                // [n] lane-interleaved decoder: where the parts of the chunk begin (lane_count<true>)
     unsigned long long *block_prefix;  // [ceil(n / kChunkThreads)] exclusive scan of per-block symbol counts
     uint32_t *changed;            // [1]
     uint32_t *max_sum;            // [1] symbols of the largest region
@@ -921,7 +921,7 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t ng = (nb + kGroupRegions - 1) / kGroupRegions;
     // exit (u8) and symbols (u16) per (chunk, entry); a map per segment of chunks and per block of segments
     const size_t transfer = chunk_bytes == kLaneBytes ? 0 : (size_t)n * kMaxStates * 3 + 64 + ((size_t)n / kSegChunks + 2 * kSegThreads + 64) * 8;
-    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 4) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * (4 + 4 + 4 + 1) + 320 + transfer;
+    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 8) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * (4 + 4 + 4 + 1) + 320 + transfer;
 }
 
 // Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
@@ -1075,8 +1075,8 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.count = reinterpret_cast<uint32_t *>(p + 64 + (size_t)nb * 8);
     a.start_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 4);
     a.exit_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 6);
-    a.mid = reinterpret_cast<uint32_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 8);
-    a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 12 + 63) & ~(size_t)63));
+    a.mid = reinterpret_cast<uint64_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 8);
+    a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 16 + 63) & ~(size_t)63));
     a.work = reinterpret_cast<uint32_t *>(a.group_prefix + (nb + 1023) / 1024 + 1);
     a.work_count = reinterpret_cast<uint32_t *>(p + 32);
     a.edge = a.work + nb + 8;
