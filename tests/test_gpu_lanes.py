@@ -93,6 +93,58 @@ def test_lane_decoder_long_codes_and_skew(codec, lanes):
     assert m == data.size and out.tobytes() == data.tobytes()
 
 
+def _handmade_stream(lengths, codes, text):
+    """file[4..] of an .et whose dictionary is given outright: lengths[s] (0 = absent), codes[s] (first bit on top)."""
+    bits = []
+
+    def put(v, n):
+        bits.extend((int(v) >> (n - 1 - i)) & 1 for i in range(n))
+
+    live = [s for s in range(256) if lengths[s]]
+    put(len(live) - 1, 8)
+    put(text.size, 32)
+    for s in live:
+        put(s, 8)
+        put(lengths[s], 8)
+        put(codes[s], int(lengths[s]))
+    bits.extend([0] * (-(len(bits) + 32) % 8))  # the four bytes before are whole
+    head = np.packbits(np.array(bits, dtype=np.uint8))
+    ln = np.asarray(lengths, dtype=np.int64)[text]
+    cd = np.asarray(codes, dtype=np.uint64)[text]
+    start = np.cumsum(ln) - ln
+    within = np.arange(int(ln.sum()), dtype=np.int64) - np.repeat(start, ln)
+    body = (np.repeat(cd, ln) >> (np.repeat(ln, ln) - 1 - within).astype(np.uint64)) & np.uint64(1)
+    return head.tobytes() + np.packbits(body.astype(np.uint8)).tobytes()
+
+
+def test_lane_decoder_deepest_codes_anywhere(codec, lanes):
+    # A chain written out by hand: symbol k is k ones and a zero, the last one all ones - codes of up to 32 bits, which a
+    # text would need 2^32 symbols to produce, here one symbol in a hundred, so that chunks in the middle of the stream
+    # (the fast walkers, both of them) meet them at every position of their windows.  The oracle reads the stream
+    # back; the library must read the same.  Beyond 32 bits the library refuses the dictionary (the reference's
+    # decoder cannot hold such a code: DESIGN.md), whatever the oracle makes of it.
+    rng = np.random.default_rng(40)
+    for depth in (20, 27, 32, 34):
+        lengths = [0] * 256
+        codes = [0] * 256
+        for k in range(depth + 1):
+            lengths[k] = min(k + 1, depth)
+            codes[k] = ((1 << k) - 1) << 1 if k < depth else (1 << depth) - 1
+        text = np.minimum(rng.geometric(0.5, 1 << 21) - 1, depth).astype(np.uint8)
+        deep = rng.random(text.size) < 0.01
+        text[deep] = rng.integers(depth - 18, depth + 1, int(deep.sum()))
+        stream = _handmade_stream(lengths, codes, text)
+        want = oracle.decode(stream, text.size)
+        assert want.tobytes() == text.tobytes(), depth  # the oracle reads it back
+        if depth > 32:
+            with pytest.raises(et.EntreepyError) as e:
+                codec.decode(stream)
+            assert e.value.name == "Unsupported"
+            continue
+        m, out = codec.decode(stream)
+        assert m == text.size and out.tobytes() == text.tobytes(), depth
+
+
 def test_lane_decoder_repairs_wrong_guesses(codec, lanes):
     # 40 of 48 symbols equiprobable: most codes have 6 or 7 bits and a wrong parse survives for a long time, so
     # the run-up guesses are often wrong and the repair rounds have to settle the entries
