@@ -39,6 +39,19 @@ namespace et {
 
 namespace {
 
+// Parts of a chunk that the lane write walk decodes side by side (et_lanes.inc).  MEASURED (r2, text-1G, all else equal):
+// two parts 0.996 ms per decode, four parts 1.012 ms - the write walk gains (wait stalls down, issue slots 59 -> 68 %) what
+// the count walk loses to recording three boundaries per chunk instead of one (four reconvergence points per chunk).
+#ifndef ET_WRITE_CHAINS
+#define ET_WRITE_CHAINS 2
+#endif
+// What the count walk records for the write walk per chunk: 18 bits per boundary.
+#if ET_WRITE_CHAINS == 2
+typedef uint32_t mid_t;
+#else
+typedef uint64_t mid_t;
+#endif
+
 constexpr uint32_t kPosMask = 0x1ffu;  // position field of a packed walk state (bit 8 = marker)
 
 struct DecArgs {
@@ -62,7 +75,7 @@ struct DecArgs {
     uint16_t *start_off;          // [n] first codeword of the chunk, bits past the chunk's first bit
     uint16_t *exit_off;           // [n] first codeword boundary at or after the chunk's end, bits past that end
     uint32_t *count;              // [n] symbols that begin inside the chunk
-    uint64_t *mid;                // [n] lane-interleaved decoder: where the parts of the chunk begin (lane_count<true>)
+    mid_t *mid;                   // [n] lane-interleaved decoder: where the parts of the chunk begin (lane_count<true>)
     unsigned long long *block_prefix;  // [ceil(n / kChunkThreads)] exclusive scan of per-block symbol counts
     uint32_t *changed;            // [1]
     uint32_t *max_sum;            // [1] symbols of the largest region
@@ -921,7 +934,7 @@ size_t unpack_scratch_bytes(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t ng = (nb + kGroupRegions - 1) / kGroupRegions;
     // exit (u8) and symbols (u16) per (chunk, entry); a map per segment of chunks and per block of segments
     const size_t transfer = chunk_bytes == kLaneBytes ? 0 : (size_t)n * kMaxStates * 3 + 64 + ((size_t)n / kSegChunks + 2 * kSegThreads + 64) * 8;
-    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + 8) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * (4 + 4 + 4 + 1) + 320 + transfer;
+    return 64 + (size_t)nb * 8 + (size_t)n * (4 + 2 + 2 + sizeof(mid_t)) + 64 + (size_t)ng * 8 + 64 + (size_t)nb * (4 + 4 + 4 + 1) + 320 + transfer;
 }
 
 // Lane-interleaved decoder: the same protocol as below with regions of 32 chunks per warp.  One extra
@@ -1075,8 +1088,8 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
     a.count = reinterpret_cast<uint32_t *>(p + 64 + (size_t)nb * 8);
     a.start_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 4);
     a.exit_off = reinterpret_cast<uint16_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 6);
-    a.mid = reinterpret_cast<uint64_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 8);
-    a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * 16 + 63) & ~(size_t)63));
+    a.mid = reinterpret_cast<mid_t *>(p + 64 + (size_t)nb * 8 + (size_t)n * 8);
+    a.group_prefix = reinterpret_cast<unsigned long long *>(p + ((64 + (size_t)nb * 8 + (size_t)n * (8 + sizeof(mid_t)) + 63) & ~(size_t)63));
     a.work = reinterpret_cast<uint32_t *>(a.group_prefix + (nb + 1023) / 1024 + 1);
     a.work_count = reinterpret_cast<uint32_t *>(p + 32);
     a.edge = a.work + nb + 8;
