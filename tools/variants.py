@@ -9,10 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "c15w14": ["ET_COUNT_BITS=15", "ET_WRITE_BITS=14"],
-    "c14w14": ["ET_COUNT_BITS=14", "ET_WRITE_BITS=14"],
-    "c15w14k4": ["ET_COUNT_BITS=15", "ET_WRITE_BITS=14", "ET_WRITE_CHAINS=4"],
-    "c15w13k2": ["ET_COUNT_BITS=15", "ET_WRITE_BITS=13"],
-    "c16w14": ["ET_COUNT_BITS=16", "ET_WRITE_BITS=14"],
+    "l25": ["ET_LANE_WORDS=25"],
+    "l29": ["ET_LANE_WORDS=29"],
+    "l21": ["ET_LANE_WORDS=21"],
 }
 if sys.argv[1] == "build":
     from entreepy_b200 import build
