@@ -179,14 +179,21 @@ __device__ __forceinline__ uint32_t long_code_add(uint32_t hi, uint32_t lo, uint
 // Returns c relative to the first word of the next piece.
 // (`last` is a run-time flag so that the body exists once: eight inlined copies of these loops
 // did not fit the instruction cache.)
+// t16_s != 0: shared address of the table of 16-bit windows (u16: bits consumed | whole codes << 9, kLutMarker when not
+// even one code begins the window) - twice the symbols per lookup for codes of about a byte; the last word of a chunk
+// still goes through the 12-bit table, which knows where to stop.
+template <bool T16 = false>
 __device__ __forceinline__ uint32_t count_piece(const uint32_t (&w)[5], uint32_t c, bool last, uint32_t clut_s,
-                                                const uint32_t *__restrict__ wlut, const uint32_t *__restrict__ nodes) {
+                                                const uint32_t *__restrict__ wlut, const uint32_t *__restrict__ nodes, uint32_t t16_s = 0) {
 #pragma unroll
     for (int wi = 0; wi < 4; ++wi) {
         const uint32_t hi = w[wi], lo = w[wi + 1];
         for (;;) {
             if (wi < 3 || !last) {
-                while (!(c & 0x1e0u)) c += lds_u16(clut_s + window_offset(hi, lo, c));
+                if (T16)
+                    while (!(c & 0x1e0u)) c += lds_u16(t16_s + ((__funnelshift_l(lo, hi, c) >> 15) & 0x1fffeu));
+                else
+                    while (!(c & 0x1e0u)) c += lds_u16(clut_s + window_offset(hi, lo, c));
             } else {
                 while ((c & kPosMask) <= (uint32_t)(32 - kLutBits)) c += lds_u16(clut_s + window_offset(hi, lo, c));
                 while (!(c & 0x1e0u)) c += lds_u16(clut_s + window_offset(hi, lo, c) + 2);
@@ -431,8 +438,9 @@ __device__ __forceinline__ void prefetch_chunk_l2(const DecArgs &a, const Chunk 
 // the walk entered the chunk; else start at `start` (bits past the chunk's first bit).
 // Chunks are whole 32-byte sectors; the stream is read a sector at a time, one sector ahead.
 // Returns the packed state relative to the chunk's end.
+template <bool T16 = false>
 __device__ __forceinline__ uint32_t count_chunk_fast(const DecArgs &a, const Chunk &k, uint32_t start, bool warm,
-                                                     uint32_t clut_s, uint32_t *entry) {
+                                                     uint32_t clut_s, uint32_t *entry, uint32_t t16_s = 0) {
     const uint64_t pair0 = k.begin >> 8;
     const uint32_t n_pairs = a.chunk_bytes >> 5;
     prefetch_chunk_l2(a, k);
@@ -460,7 +468,7 @@ __device__ __forceinline__ uint32_t count_chunk_fast(const DecArgs &a, const Chu
         } else {
             w[0] = cur.b.x; w[1] = cur.b.y; w[2] = cur.b.z; w[3] = cur.b.w; w[4] = bswap32(raw.a.x);
         }
-        c = count_piece(w, c, p + 1 == n_pieces, clut_s, a.wlut, a.nodes);
+        c = count_piece<T16>(w, c, p + 1 == n_pieces, clut_s, a.wlut, a.nodes, t16_s);
     }
     return c;
 }
@@ -829,6 +837,42 @@ __global__ void __launch_bounds__(256) build_sub_tables_kernel(const uint32_t *_
 
 #include "et_lanes.inc"
 
+// The transfer-function walks with two tables in shared memory: the 16-bit windows (128 KiB: two codes of a byte per
+// lookup where the 12-bit table of chunk_transfer_kernel gives one) and the 12-bit table for the last word of a chunk.
+// One persistent CTA of 1024 threads per SM (the tables are loaded once), a thread per (chunk, entry), last chunks first.
+constexpr uint32_t kCount16TableBytes = (1u << 16) * 2;
+constexpr uint32_t kTransfer16Threads = 1024;
+__global__ void __launch_bounds__(kTransfer16Threads, 1) chunk_transfer16_kernel(const DecArgs a, uint32_t s_log2, uint32_t n_states,
+                                                                                const uint16_t *__restrict__ t16) {
+    extern __shared__ __align__(16) uint8_t dyn[];
+    uint32_t *clut_sh = reinterpret_cast<uint32_t *>(dyn + kCount16TableBytes);
+    table_to_shared(dyn, t16, kCount16TableBytes);
+    for (int i = threadIdx.x; i < kLutSize; i += kTransfer16Threads) clut_sh[i] = a.clut[i];
+    __syncthreads();
+    const uint32_t t16_s = smem_addr(dyn), clut_s = smem_addr(clut_sh);
+    const uint64_t total = (uint64_t)a.n_chunks << s_log2;
+    for (uint64_t item = (uint64_t)blockIdx.x * kTransfer16Threads + threadIdx.x; item < total; item += (uint64_t)gridDim.x * kTransfer16Threads) {
+        const uint32_t idx = (uint32_t)(total - 1u - item);
+        const uint32_t c = idx >> s_log2, e = idx & ((1u << s_log2) - 1u);
+        if (c == 0 || e >= n_states) continue;  // chunk 0 is entered at the head: chunk_sync_kernel walks it
+        const Chunk k = chunk_of(a, c);
+        uint32_t cnt = 0, exit_bits = 0;
+        if (k.walkable) {
+            uint32_t entry;
+            const uint32_t s = count_chunk_fast<true>(a, k, e, false, clut_s, &entry, t16_s);
+            cnt = s >> 9;
+            exit_bits = s & kPosMask;
+        } else {
+            uint64_t pos = k.begin + e;
+            uint32_t bad = 0;
+            if (pos < k.end) pos = walk_generic<false>(a, pos, k.end, a.end_bit, &cnt, 0, &bad, clut_sh);
+            exit_bits = pos > k.end ? (uint32_t)(pos - k.end) : 0u;
+        }
+        a.tr_exit[idx] = (uint8_t)(exit_bits < n_states ? exit_bits : 0xFFu);
+        a.tr_cnt[idx] = (uint16_t)cnt;
+    }
+}
+
 uint64_t chunk_count(const UnpackGeometry &g, uint32_t chunk_bytes) {
     const uint64_t grid_bit = g.own_begin_bit / 256 * 256;
     const uint64_t bits = (uint64_t)chunk_bytes * 8;
@@ -845,10 +889,12 @@ cudaError_t unpack_init_device(int device, UnpackTuning *tune) {
     if ((err = cudaDeviceGetAttribute(&tune->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(region_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tune->max_smem)) != cudaSuccess)
         return err;
+    if ((err = cudaFuncSetAttribute(chunk_transfer16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tune->max_smem)) != cudaSuccess)
+        return err;
     if ((err = cudaFuncSetAttribute(region_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tune->max_smem)) != cudaSuccess)
         return err;
     // the lane-interleaved decoder's tables, built on the device for every stream (lane_tables_kernel)
-    return cudaMalloc(&tune->d_lane_tables, kCountTableBytes + kWriteTableBytes + kSingleTableBytes);
+    return cudaMalloc(&tune->d_lane_tables, kCountTableBytes + kWriteTableBytes + kSingleTableBytes + kCount16TableBytes);
 }
 void unpack_free_device(UnpackTuning *tune) {
     if (tune->d_lane_tables) cudaFree(tune->d_lane_tables);
@@ -959,7 +1005,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
     }
     am.dbg = d_dbg;
     lane_tables_kernel<<<(1u << 16) / 256, 256, 0, stream>>>(a.nodes, const_cast<uint16_t *>(a.t_count), const_cast<uint32_t *>(a.t_write),
-                                                            const_cast<uint8_t *>(a.t_single));
+                                                            const_cast<uint8_t *>(a.t_single), nullptr);
     if (launches) *launches += 1;
     const uint32_t check_grid = (n_regions + 31u) / 32u;  // 8 warps x 4 regions per CTA
     // one repair round: list the regions with a wrong entry, walk those again from their neighbours' exits
@@ -1117,7 +1163,14 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
         while ((1u << s_log2) < transfer_states) ++s_log2;
         chunk_sync_kernel<<<1, kChunkThreads, 0, stream>>>(a, 0, 1u);  // chunk 0 from the head (or from its guess, for a shard)
         const uint64_t threads = (uint64_t)n << s_log2;
-        chunk_transfer_kernel<<<(unsigned)((threads + kChunkThreads - 1) / kChunkThreads), kChunkThreads, 0, stream>>>(a, s_log2, transfer_states);
+        if (tune.d_lane_tables && threads >= (uint64_t)tune.num_sms * kTransfer16Threads * 4 &&
+            (size_t)tune.max_smem >= kCount16TableBytes + kLutSize * 4u) {
+            uint16_t *t16 = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(tune.d_lane_tables) + kCountTableBytes + kWriteTableBytes + kSingleTableBytes);
+            lane_tables_kernel<<<(1u << 16) / 256, 256, 0, stream>>>(a.nodes, nullptr, nullptr, nullptr, t16);
+            chunk_transfer16_kernel<<<tune.num_sms, kTransfer16Threads, kCount16TableBytes + kLutSize * 4u, stream>>>(a, s_log2, transfer_states, t16);
+            if (launches) *launches += 1;
+        } else
+            chunk_transfer_kernel<<<(unsigned)((threads + kChunkThreads - 1) / kChunkThreads), kChunkThreads, 0, stream>>>(a, s_log2, transfer_states);
         const uint32_t seg_blocks = (n + kSegChunks * kSegThreads - 1) / (kSegChunks * kSegThreads);
         unsigned long long *seg_prefix = reinterpret_cast<unsigned long long *>(a.tr_cnt + ((size_t)n << s_log2)) ;
         seg_prefix = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(seg_prefix) + 7) & ~(uintptr_t)7);
