@@ -178,6 +178,34 @@ __device__ __forceinline__ void push_acc(BitAcc &b, uint32_t code, uint32_t len)
     b.pos = p2;
 }
 
+// {code, length} of symbol k (0..3, first in the lowest byte) of text word w from the lane's column of the shared table
+// (tab_lane_s: its shared address).  One byte permute and one multiply-add per symbol - symbol x 128 + column, the
+// multiplier in a register (`r128`, a value the assembler cannot know, or it turns the multiply into a shift and an add) -
+// where shift, mask, OR of the lane's offset and add of the base were four instructions, three of them for the ALU pipe.
+template <int K>
+__device__ __forceinline__ uint2 table_entry(uint32_t w, uint32_t tab_lane_s, uint32_t r128) {
+    const uint32_t sym = K == 0 ? (w & 0xffu) : K == 3 ? (w >> 24) : __byte_perm(w, 0u, 0x4440u + K);
+    uint32_t addr;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(sym), "r"(r128), "r"(tab_lane_s));
+    uint2 e;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr));
+    return e;
+}
+__device__ __forceinline__ uint32_t opaque_128(const PackArgs &a) {
+    uint32_t v = a.image_words ? 128u : 129u;  // image_words is never 0
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
+template <int K>
+__device__ __forceinline__ uint32_t table_length(uint32_t w, uint32_t len_lane_s, uint32_t r128) {  // the same for pass A's [symbol][lane] table of lengths
+    const uint32_t sym = K == 0 ? (w & 0xffu) : K == 3 ? (w >> 24) : __byte_perm(w, 0u, 0x4440u + K);
+    uint32_t addr, len;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(sym), "r"(r128), "r"(len_lane_s));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(len) : "r"(addr));
+    return len;
+}
+
 // Pass A, a warp per region: four coalesced 16-byte loads per lane, a run's bit count is the sum over the four lanes that
 // hold it (two shuffles), and nothing in the kernel waits for anything - no barrier, no running total carried by one
 // thread (round 1's slab form, 4096 symbols per CTA step with the group's running total kept
@@ -189,6 +217,7 @@ __global__ void __launch_bounds__(kPackThreads) region_bits_kernel(const PackArg
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     const uint8_t *len_lane = reinterpret_cast<const uint8_t *>(len_sh) + lane * 4;
+    const uint32_t len_lane_s = (uint32_t)__cvta_generic_to_shared(len_lane), r128 = opaque_128(a);
     const uint32_t stride = gridDim.x * kWarps;
     for (uint32_t r = blockIdx.x * kWarps + (threadIdx.x >> 5); r < a.n_regions; r += stride) {
         if (region_is_interior(a, r)) {
@@ -204,10 +233,8 @@ __global__ void __launch_bounds__(kPackThreads) region_bits_kernel(const PackArg
                 uint32_t bits = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    bits += *reinterpret_cast<const uint32_t *>(len_lane + ((w[q] << 7) & 0x7f80u)) +
-                            *reinterpret_cast<const uint32_t *>(len_lane + ((w[q] >> 1) & 0x7f80u)) +
-                            *reinterpret_cast<const uint32_t *>(len_lane + ((w[q] >> 9) & 0x7f80u)) +
-                            *reinterpret_cast<const uint32_t *>(len_lane + ((w[q] >> 17) & 0x7f80u));
+                    bits += table_length<0>(w[q], len_lane_s, r128) + table_length<1>(w[q], len_lane_s, r128) +
+                            table_length<2>(w[q], len_lane_s, r128) + table_length<3>(w[q], len_lane_s, r128);
                 bits += __shfl_xor_sync(0xffffffffu, bits, 1);
                 bits += __shfl_xor_sync(0xffffffffu, bits, 2);  // the run's bits, in its four lanes
                 if ((lane & 3u) == 0) a.run_bits[(size_t)r * 32 + 8 * i + (lane >> 2)] = (uint16_t)bits;
@@ -274,8 +301,9 @@ __device__ __forceinline__ void load_run(const PackArgs &a, uint32_t r, uint32_t
 
 // The 64 symbols of a lane's run through the accumulator (their codes from the lane's column of the shared table).
 __device__ __forceinline__ void pack_run_symbols(BitAcc &acc, const uint4 (&raw)[4], unsigned long long valid, bool interior,
-                                                 const uint8_t *table_lane) {
+                                                 const uint8_t *table_lane, uint32_t r128) {
     if (interior) {
+        const uint32_t tab_lane_s = (uint32_t)__cvta_generic_to_shared(table_lane);
         uint4 v0 = raw[0], v1 = raw[1], v2 = raw[2], v3 = raw[3];
 #pragma unroll 1
         for (int it = 0; it < 4; ++it) {  // one 16-byte vector per trip: the body must stay inside the instruction cache
@@ -285,10 +313,8 @@ __device__ __forceinline__ void pack_run_symbols(BitAcc &acc, const uint4 (&raw)
                 const uint32_t w = rw[q];
                 // the four symbols of a word: their codes are merged in registers and go into the accumulator
                 // as ONE piece when they fit 32 bits together (text: ~19 bits), else as two pairs, else one by one
-                const uint2 e0 = *reinterpret_cast<const uint2 *>(table_lane + ((w << 7) & 0x7f80u));
-                const uint2 e1 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 1) & 0x7f80u));
-                const uint2 e2 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 9) & 0x7f80u));
-                const uint2 e3 = *reinterpret_cast<const uint2 *>(table_lane + ((w >> 17) & 0x7f80u));
+                const uint2 e0 = table_entry<0>(w, tab_lane_s, r128), e1 = table_entry<1>(w, tab_lane_s, r128);
+                const uint2 e2 = table_entry<2>(w, tab_lane_s, r128), e3 = table_entry<3>(w, tab_lane_s, r128);
                 const uint32_t l01 = e0.y + e1.y, l23 = e2.y + e3.y, len = l01 + l23;
                 if (len <= 32u) {
                     const uint32_t c01 = __funnelshift_lc(0u, e0.x, e1.y) | e1.x, c23 = __funnelshift_lc(0u, e2.x, e3.y) | e3.x;
@@ -420,6 +446,7 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
     }
     __syncthreads();
     const uint8_t *table_lane = table + (lane & (kTableLanes - 1)) * 8;
+    const uint32_t r128 = opaque_128(a);
     const uint32_t stride = gridDim.x * kRunWarps;
     uint32_t r = blockIdx.x * kRunWarps + warp;
     if (r >= a.n_regions) return;
@@ -478,7 +505,7 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
             BitAcc acc;
             acc.hi = acc.lo = 0;
             acc.pos = (uint32_t)__cvta_generic_to_shared(stage + kStageGuard) * 8u + my_off;
-            pack_run_symbols(acc, raw, valid, interior, table_lane);
+            pack_run_symbols(acc, raw, valid, interior, table_lane, r128);
             __syncwarp();  // every whole word is in place
             if (acc.pos & 31u) atomicOr(stage + kStageGuard + ((my_off + my_bits) >> 5), acc.lo << (32u - (acc.pos & 31u)));
         }
@@ -539,6 +566,7 @@ __global__ void __launch_bounds__(kTileMaxWarps * 32, 1) pack_tiles_kernel(const
     }
     __syncthreads();
     const uint8_t *table_lane = table + (lane & (kTableLanes - 1)) * 8;
+    const uint32_t r128 = opaque_128(a);
     const uint32_t priv_bit0 = (uint32_t)__cvta_generic_to_shared(priv) * 8u;
 
     for (;;) {
@@ -556,7 +584,7 @@ __global__ void __launch_bounds__(kTileMaxWarps * 32, 1) pack_tiles_kernel(const
             BitAcc acc;
             acc.hi = acc.lo = 0;
             acc.pos = priv_bit0;
-            pack_run_symbols(acc, raw, valid, interior, table_lane);
+            pack_run_symbols(acc, raw, valid, interior, table_lane, r128);
             my_bits = acc.pos - priv_bit0;
             if (my_bits & 31u) priv[my_bits >> 5] = acc.lo << (32u - (my_bits & 31u));  // the unfinished last word, zero padded
         }
