@@ -356,6 +356,14 @@ __device__ __forceinline__ void pack_run_symbols(BitAcc &acc, const uint4 (&raw)
 // The finished bit image of region r (region bit b in word kStageGuard + (b >> 5), MSB first) goes to its place in the
 // output: shifted to the region's final bit position, swapped to stream order, stored as aligned 16-byte vectors; the
 // (at most two) bytes it shares with its neighbours go to the seam arrays.
+// Frame: the 16-byte blocks of the output that the region touches; frame bit of region bit 0 (< 128):
+__device__ __forceinline__ uint32_t region_frame_shift(const PackArgs &a, unsigned long long bit_begin) {
+    return (uint32_t)(reinterpret_cast<uintptr_t>(a.out + (bit_begin >> 3)) & 15u) * 8u + (uint32_t)(bit_begin & 7);
+}
+// IN_FRAME: the image was assembled at frame positions already (image bit = frame bit: pack_runs_kernel knows where the
+// region goes before it packs), so a block of the output is four image words as they stand; else the image starts at
+// region bit 0 and is funnel-shifted here.
+template <bool IN_FRAME = false>
 __device__ __forceinline__ void region_copy_out(const PackArgs &a, uint32_t r, const uint32_t *stage, uint8_t *edge,
                                                 unsigned long long bit_begin, uint32_t region_bits, uint32_t lane) {
     const unsigned long long bit_end = bit_begin + region_bits;
@@ -385,9 +393,13 @@ __device__ __forceinline__ void region_copy_out(const PackArgs &a, uint32_t r, c
         const uint32_t bs = shift & 31u, ws = shift >> 5;
         for (uint32_t c = lane; c < n_chunks; c += 32) {
             const uint4 *src = reinterpret_cast<const uint4 *>(stage + kStageGuard) + c;
-            const uint4 p = src[-1], q = src[0];
+            const uint4 q = src[0];
+            uint4 p = q;
+            if (!IN_FRAME) p = src[-1];
             uint32_t f0, f1, f2, f3;
-            switch (ws) {
+            if (IN_FRAME) {
+                f0 = q.x; f1 = q.y; f2 = q.z; f3 = q.w;
+            } else switch (ws) {
                 case 0:
                     f0 = __funnelshift_r(q.x, p.w, bs); f1 = __funnelshift_r(q.y, q.x, bs);
                     f2 = __funnelshift_r(q.z, q.y, bs); f3 = __funnelshift_r(q.w, q.z, bs);
@@ -500,17 +512,20 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
         {
             // the word in which the region ends is only ever ORed into (or not touched at all), and the byte in which
             // it ends may reach into the word after it: both start from zero
-            if (lane < 2) stage[kStageGuard + (region_bits >> 5) + lane] = 0;
+            // (the image is assembled at the positions of the output frame - region bit 0 at bit `shift` - so that the
+            // copy-out has nothing to shift; what lies before the region's first bit in its first block is never stored)
+            const uint32_t shift = region_frame_shift(a, bit_begin);
+            if (lane < 2) stage[kStageGuard + ((shift + region_bits) >> 5) + lane] = 0;
             __syncwarp();
             BitAcc acc;
             acc.hi = acc.lo = 0;
-            acc.pos = (uint32_t)__cvta_generic_to_shared(stage + kStageGuard) * 8u + my_off;
+            acc.pos = (uint32_t)__cvta_generic_to_shared(stage + kStageGuard) * 8u + shift + my_off;
             pack_run_symbols(acc, raw, valid, interior, table_lane, r128);
             __syncwarp();  // every whole word is in place
-            if (acc.pos & 31u) atomicOr(stage + kStageGuard + ((my_off + my_bits) >> 5), acc.lo << (32u - (acc.pos & 31u)));
+            if (acc.pos & 31u) atomicOr(stage + kStageGuard + ((shift + my_off + my_bits) >> 5), acc.lo << (32u - (acc.pos & 31u)));
         }
         __syncwarp();  // image complete
-        region_copy_out(a, r, stage, edge, bit_begin, region_bits, lane);
+        region_copy_out<true>(a, r, stage, edge, bit_begin, region_bits, lane);
         __syncwarp();  // everyone has read the image
         if (r_next >= a.n_regions) break;
         r = r_next;
