@@ -168,13 +168,21 @@ __device__ __forceinline__ bool region_is_interior(const PackArgs &a, uint32_t r
 // (pack_runs_kernel), so every word of the image is written exactly once and ORed at most a few times.
 struct BitAcc {
     uint32_t hi, lo, pos;
+    uint32_t wp;  // shared address of the word that holds bit `pos` (kept beside pos: deriving it is a shift and a mask per store)
 };
+__device__ __forceinline__ void open_acc(BitAcc &b, uint32_t bit_address) {
+    b.hi = b.lo = 0;
+    b.pos = bit_address;
+    b.wp = (bit_address >> 3) & ~3u;
+}
 __device__ __forceinline__ void push_acc(BitAcc &b, uint32_t code, uint32_t len) {
     b.hi = __funnelshift_lc(b.lo, b.hi, len);
     b.lo = __funnelshift_lc(0u, b.lo, len) | code;
     const uint32_t p2 = b.pos + len;
-    if ((b.pos ^ p2) & 32u)
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(((p2 >> 3) & ~3u) - 4u), "r"(__funnelshift_r(b.lo, b.hi, p2)) : "memory");
+    if ((b.pos ^ p2) & 32u) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(b.wp), "r"(__funnelshift_r(b.lo, b.hi, p2)) : "memory");
+        b.wp += 4u;
+    }
     b.pos = p2;
 }
 
@@ -518,8 +526,7 @@ __global__ void __launch_bounds__(kRunWarps * 32, 2) pack_runs_kernel(const Pack
             if (lane < 2) stage[kStageGuard + ((shift + region_bits) >> 5) + lane] = 0;
             __syncwarp();
             BitAcc acc;
-            acc.hi = acc.lo = 0;
-            acc.pos = (uint32_t)__cvta_generic_to_shared(stage + kStageGuard) * 8u + shift + my_off;
+            open_acc(acc, (uint32_t)__cvta_generic_to_shared(stage + kStageGuard) * 8u + shift + my_off);
             pack_run_symbols(acc, raw, valid, interior, table_lane, r128);
             __syncwarp();  // every whole word is in place
             if (acc.pos & 31u) atomicOr(stage + kStageGuard + ((shift + my_off + my_bits) >> 5), acc.lo << (32u - (acc.pos & 31u)));
@@ -597,8 +604,7 @@ __global__ void __launch_bounds__(kTileMaxWarps * 32, 1) pack_tiles_kernel(const
             unsigned long long valid;
             load_run(a, r, lane, interior, raw, &valid);
             BitAcc acc;
-            acc.hi = acc.lo = 0;
-            acc.pos = priv_bit0;
+            open_acc(acc, priv_bit0);
             pack_run_symbols(acc, raw, valid, interior, table_lane, r128);
             my_bits = acc.pos - priv_bit0;
             if (my_bits & 31u) priv[my_bits >> 5] = acc.lo << (32u - (my_bits & 31u));  // the unfinished last word, zero padded
