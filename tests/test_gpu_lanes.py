@@ -156,3 +156,37 @@ def test_lane_decoder_repairs_wrong_guesses(codec, lanes):
     assert int(lengths.max()) - int(lengths[lengths > 0].min()) > 2
     m, out = codec.decode(_oracle_et(data)[4:])
     assert m == data.size and out.tobytes() == data.tobytes()
+
+
+def test_lane_decoder_survives_random_bodies(codec, lanes):
+    # Random bytes behind a dictionary: with a complete code every bit pattern decodes to something (compare with the
+    # oracle); with an incomplete one the walkers meet patterns that are no code at all, everywhere in their windows.
+    # The call must come back (an answer or Corrupt) and the context must still decode a good stream afterwards - a
+    # walk that leaves its shared memory would poison the CUDA context for good.
+    rng = np.random.default_rng(77)
+    good = rng.choice(64, 1 << 20, p=(lambda w: w / w.sum())(rng.random(64) ** 3)).astype(np.uint8)
+    good[:64] = np.arange(64, dtype=np.uint8)
+    good_stream = _oracle_et(good)[4:]
+    for trial in range(6):
+        n_syms = int(rng.integers(3, 31))  # codes of up to 30 bits
+        lengths = [0] * 256
+        codes = [0] * 256
+        # a chain code (prefix-free); dropping the all-ones leaf makes it incomplete
+        for k in range(n_syms):
+            lengths[k] = min(k + 1, n_syms - 1) if trial % 2 == 0 else k + 1
+            codes[k] = ((1 << k) - 1) << 1 if (k < n_syms - 1 or trial % 2) else (1 << (n_syms - 1)) - 1
+        body = rng.integers(0, 256, int(rng.integers(200_000, 900_000)), dtype=np.uint8)
+        if trial % 2:  # incomplete: long runs of ones are no code
+            body[rng.integers(0, body.size, body.size // 50)] = 0xFF
+        head = _handmade_stream(lengths, codes, np.zeros(1, dtype=np.uint8))
+        n_claim = body.size * 3
+        stream = bytes([head[0]]) + int(n_claim).to_bytes(4, "big") + head[5:-1] + body.tobytes()
+        try:
+            m, out = codec.decode(stream)
+            if trial % 2 == 0:
+                want = oracle.decode(stream, n_claim)
+                assert m == want.size and out.tobytes() == want.tobytes(), trial
+        except et.EntreepyError as e:
+            assert e.name in ("Corrupt", "NoSpaceLeft"), (trial, e.name)
+        m, out = codec.decode(good_stream)
+        assert m == good.size and out.tobytes() == good.tobytes(), trial
