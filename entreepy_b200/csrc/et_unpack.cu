@@ -119,11 +119,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 // Loads from the decode tables: filled once per CTA before the walks, read-only afterwards, so the
 // compiler may schedule these freely among the (volatile) stores of the text.
-__device__ __forceinline__ uint32_t lds_tab_u32(uint32_t addr) {
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ uint32_t lds_tab_u16(uint32_t addr) {
     uint32_t v;
     asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -844,7 +839,7 @@ constexpr uint32_t kCount16TableBytes = (1u << 16) * 2;
 constexpr uint32_t kTransfer16Threads = 1024;
 __global__ void __launch_bounds__(kTransfer16Threads, 1) chunk_transfer16_kernel(const DecArgs a, uint32_t s_log2, uint32_t n_states,
                                                                                 const uint16_t *__restrict__ t16) {
-    extern __shared__ __align__(16) uint8_t dyn[];
+    extern __shared__ __align__(128) uint8_t dyn[];
     uint32_t *clut_sh = reinterpret_cast<uint32_t *>(dyn + kCount16TableBytes);
     table_to_shared(dyn, t16, kCount16TableBytes);
     for (int i = threadIdx.x; i < kLutSize; i += kTransfer16Threads) clut_sh[i] = a.clut[i];
