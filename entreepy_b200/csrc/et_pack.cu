@@ -227,13 +227,26 @@ __global__ void __launch_bounds__(kPackThreads) region_bits_kernel(const PackArg
     const uint8_t *len_lane = reinterpret_cast<const uint8_t *>(len_sh) + lane * 4;
     const uint32_t len_lane_s = (uint32_t)__cvta_generic_to_shared(len_lane), r128 = opaque_128(a);
     const uint32_t stride = gridDim.x * kWarps;
+    // coalesced: load i of lane L is vector 32 i + L of the region, i.e. a quarter of run 8 i + L / 4 (a lane loading
+    // its own run, 64 bytes apart from its neighbour's, fetches every 32-byte sector twice from L2: measured 2.09 GB
+    // of L2 traffic per GiB and an L2-bound kernel).  The next region's vectors are requested before this one's are used.
+    uint4 nv[4];
+    bool have = false;
+    auto request = [&](uint32_t rr) {
+        have = rr < a.n_regions && region_is_interior(a, rr);
+        if (have) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.in_aligned + (uint64_t)rr * kRegionSyms) + lane;
+            nv[0] = ld_stream_v4(src);
+            nv[1] = ld_stream_v4(src + 32);
+            nv[2] = ld_stream_v4(src + 64);
+            nv[3] = ld_stream_v4(src + 96);
+        }
+    };
+    request(blockIdx.x * kWarps + (threadIdx.x >> 5));
     for (uint32_t r = blockIdx.x * kWarps + (threadIdx.x >> 5); r < a.n_regions; r += stride) {
-        if (region_is_interior(a, r)) {
-            // coalesced: load i of lane L is vector 32 i + L of the region, i.e. a quarter of run 8 i + L / 4 (a lane loading
-            // its own run, 64 bytes apart from its neighbour's, fetches every 32-byte sector twice from L2: measured 2.09 GB
-            // of L2 traffic per GiB and an L2-bound kernel)
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.in_aligned + (uint64_t)r * kRegionSyms) + lane;
-            const uint4 v[4] = {ld_stream_v4(src), ld_stream_v4(src + 32), ld_stream_v4(src + 64), ld_stream_v4(src + 96)};
+        if (have) {
+            const uint4 v[4] = {nv[0], nv[1], nv[2], nv[3]};
+            request(r + stride);
             uint32_t total = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -261,6 +274,7 @@ __global__ void __launch_bounds__(kPackThreads) region_bits_kernel(const PackArg
         a.run_bits[(size_t)r * 32 + lane] = (uint16_t)bits;
         const uint32_t total = __reduce_add_sync(0xffffffffu, bits);
         if (lane == 0) a.tile_bits[r] = total;
+        request(r + stride);
     }
 }
 // tile_bits[r]: the region's bits -> bits of the regions before it inside its group of kPrefixGroup; group_prefix[g]: the
@@ -983,7 +997,9 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         a.group_shift = 10;
         const uint32_t groups = (n_regions + kPrefixGroup - 1) / kPrefixGroup;
         {
-            unsigned pa_grid = (unsigned)num_sms * 6u;  // 6 CTAs of 8 warps per SM: the 32 KB table and 48 registers allow it
+            int per_sm = 0;  // CTAs of 8 warps that fit an SM (32 KB table each, 48 registers per thread: five)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, region_bits_kernel, kPackThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+            unsigned pa_grid = (unsigned)num_sms * (unsigned)per_sm;
             const unsigned need = (n_regions + kWarps - 1) / kWarps;
             if (pa_grid > need) pa_grid = need;
             region_bits_kernel<<<pa_grid, kPackThreads, 0, stream>>>(a);
