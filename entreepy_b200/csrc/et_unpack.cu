@@ -942,7 +942,9 @@ UnpackGeometry unpack_geometry_shard(const void *d_range, size_t range_bytes, si
 static uint64_t lane_path_min_bytes(const UnpackTuning &tune) {
     if (tune.lane_min_bytes >= 0)
         return (uint64_t)tune.lane_min_bytes > 2 * kRegionBytes ? (uint64_t)tune.lane_min_bytes : 2 * kRegionBytes;
-    return (uint64_t)tune.num_sms * 8 * kRegionBytes;
+    // MEASURED (r2, text): below ~2 MB of stream the per-thread kernels are as fast or faster (fewer launches, smaller tables
+    // to load); 1.2 MB: 0.135 ms against 0.144, 2.5 MB: 0.148 against 0.132, 4.9 MB: 0.171 against 0.119
+    return (uint64_t)tune.num_sms * 3 * kRegionBytes;
 }
 
 // Chunk size.  256 B suits codes that re-synchronise within a few symbols.  When all code
@@ -990,6 +992,12 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
     if (sync_warps > kMaxLaneWarps) sync_warps = kMaxLaneWarps;
     if (tune.sync_warps > 0 && (uint32_t)tune.sync_warps < sync_warps) sync_warps = (uint32_t)tune.sync_warps;
     if (sync_warps > 4) sync_warps &= ~3u;  // the same number of warps on each of the SM's four schedulers: they share the regions evenly
+    // a stream with fewer regions than the GPU has warps for: a few warps on every SM rather than full CTAs on a few SMs
+    auto spread = [&](uint32_t warps_max) {
+        uint32_t w = ((n_regions + (uint32_t)num_sms - 1) / (uint32_t)num_sms + 3u) & ~3u;
+        return w < 4u ? 4u : w > warps_max ? warps_max : w;
+    };
+    if (sync_warps > 4) sync_warps = spread(sync_warps);
     const uint32_t sync_smem = kSyncTableBytes + sync_warps * kImgBytes;
     const uint32_t sync_blocks = (n_regions + sync_warps - 1) / sync_warps;
     const uint32_t sync_grid = sync_blocks < (uint32_t)num_sms ? sync_blocks : (uint32_t)num_sms;
@@ -1026,9 +1034,10 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
         region_sum_kernel<<<n_groups, 1024, 0, stream>>>(a, n_regions);
         chunk_scan_kernel<<<1, 1024, 0, stream>>>(a, a.group_prefix, n_groups);
         region_apply_kernel<<<n_groups, 1024, 0, stream>>>(a, n_regions);
-        const uint32_t write_blocks = (n_regions + 15u) / 16u;
+        const uint32_t write_warps = spread(tune.write_warps > 0 ? (uint32_t)tune.write_warps : 16u);
+        const uint32_t write_blocks = (n_regions + write_warps - 1) / write_warps;
         region_write_kernel<<<write_blocks < (uint32_t)num_sms ? write_blocks : (uint32_t)num_sms, 512, max_smem, stream>>>(
-            a, n_regions, (uint32_t)max_smem, tune.write_warps > 0 ? (uint32_t)tune.write_warps : 16u);
+            a, n_regions, (uint32_t)max_smem, write_warps);
         if (launches) *launches += 4;
         // one look at the scratch header: error flags, symbols found, "an entry was wrong", entry and exit of the shard
         if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;

@@ -31,6 +31,8 @@ if os.environ.get("ET_WRITE_WARPS"):
     c.set_tuning(et._abi.TUNE_WRITE_WARPS, int(os.environ["ET_WRITE_WARPS"]))
 if os.environ.get("ET_SYNC_WARPS"):
     c.set_tuning(et._abi.TUNE_SYNC_WARPS, int(os.environ["ET_SYNC_WARPS"]))
+if os.environ.get("ET_LANE_MIN_BYTES"):
+    c.set_tuning(et._abi.TUNE_LANE_MIN_BYTES, int(os.environ["ET_LANE_MIN_BYTES"]))
 if os.environ.get("ET_PACK_SINGLE_PASS"):
     c.set_tuning(et._abi.TUNE_PACK_SINGLE_PASS, 1)
 dev = torch.empty(n, dtype=torch.uint8, device="cuda")
