@@ -468,35 +468,9 @@ __device__ __forceinline__ uint32_t count_chunk_fast(const DecArgs &a, const Chu
     return c;
 }
 
-__global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecArgs a, int round, uint32_t only_below = 0xFFFFFFFFu) {
-    __shared__ __align__(16) uint32_t clut_sh[kLutSize];
-    const uint32_t c = blockIdx.x * kChunkThreads + threadIdx.x;
-    uint32_t start = 0;
-    bool work = c < a.n_chunks && c < only_below;
-    if (work && round != 0) {
-        if (c == 0) {
-            work = false;
-        } else {
-            start = a.exit_off[c - 1];
-            work = start != a.start_off[c];
-        }
-    }
-    if (!__syncthreads_or(work)) return;  // later rounds touch only the chunks whose entry moved
-    for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) clut_sh[i] = a.clut[i];
-    __syncthreads();
-    if (!work) return;
-    if (round != 0) *a.changed = 1u;
+// The count walk of chunk c from `start` (known: a proven boundary; else a guess, and the walk begins 128 bits early).
+__device__ __forceinline__ void sync_chunk(const DecArgs &a, uint32_t c, uint32_t start, bool known, const uint32_t *clut_sh) {
     const Chunk k = chunk_of(a, c);
-    if (c == 0 && a.head_known) start = a.head_off;
-    bool known = round != 0 || (c == 0 && a.head_known);
-    if (a.fixed_len && round == 0) {
-        // Codes of one length never re-synchronise (a wrong phase stays wrong for ever), but they need not: every
-        // boundary is a whole number of codes past the first one.  Without a known head the first entry is a guess
-        // (bit 0 of the owned part); the others are consistent with it, and the caller repairs the guess.
-        const uint64_t base = a.grid_bit + (a.head_known ? a.head_off : 0u);
-        if (k.begin > base) start = (uint32_t)((a.fixed_len - (k.begin - base) % a.fixed_len) % a.fixed_len);
-        known = true;
-    }
     uint32_t cnt = 0, entry = start, exit_bits = 0;
     if (k.interior || (known && k.walkable && start < 256u)) {
         const uint32_t s = count_chunk_fast(a, k, start, !known, smem_addr(clut_sh), &entry);
@@ -518,6 +492,37 @@ __global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecA
     a.count[c] = cnt;
 }
 
+__global__ void __launch_bounds__(kChunkThreads, 6) chunk_sync_kernel(const DecArgs a, int round) {
+    __shared__ __align__(16) uint32_t clut_sh[kLutSize];
+    const uint32_t c = blockIdx.x * kChunkThreads + threadIdx.x;
+    uint32_t start = 0;
+    bool work = c < a.n_chunks;
+    if (work && round != 0) {
+        if (c == 0) {
+            work = false;
+        } else {
+            start = a.exit_off[c - 1];
+            work = start != a.start_off[c];
+        }
+    }
+    if (!__syncthreads_or(work)) return;  // later rounds touch only the chunks whose entry moved
+    for (int i = threadIdx.x; i < kLutSize; i += kChunkThreads) clut_sh[i] = a.clut[i];
+    __syncthreads();
+    if (!work) return;
+    if (round != 0) *a.changed = 1u;
+    if (c == 0 && a.head_known) start = a.head_off;
+    bool known = round != 0 || (c == 0 && a.head_known);
+    if (a.fixed_len && round == 0) {
+        // Codes of one length never re-synchronise (a wrong phase stays wrong for ever), but they need not: every
+        // boundary is a whole number of codes past the first one.  Without a known head the first entry is a guess
+        // (bit 0 of the owned part); the others are consistent with it, and the caller repairs the guess.
+        const uint64_t begin = chunk_of(a, c).begin, base = a.grid_bit + (a.head_known ? a.head_off : 0u);
+        if (begin > base) start = (uint32_t)((a.fixed_len - (begin - base) % a.fixed_len) % a.fixed_len);
+        known = true;
+    }
+    sync_chunk(a, c, start, known, clut_sh);
+}
+
 // ------------------------------------------------------------------ transfer functions (slowly synchronising codes)
 // Codes whose lengths are nearly equal (uniform bytes: 7 and 8 bits) re-synchronise after kilobytes, sometimes after
 // a hundred: the repair rounds above then walk the longest unsynchronised stretch one chunk per round, a sequential
@@ -533,7 +538,11 @@ __global__ void __launch_bounds__(kChunkThreads, 6) chunk_transfer_kernel(const 
     __syncthreads();
     const uint32_t idx = (gridDim.x - 1u - blockIdx.x) * kChunkThreads + threadIdx.x;  // last chunks first: the stream's ragged end is the slow one
     const uint32_t c = idx >> s_log2, e = idx & ((1u << s_log2) - 1u);
-    if (c == 0 || c >= a.n_chunks || e >= n_states) return;  // chunk 0 is entered at the head: chunk_sync_kernel walks it
+    if (c >= a.n_chunks || e >= n_states) return;
+    if (c == 0) {  // chunk 0 is entered at the head of the stream (or at its guess, for a shard): one walk, what the scan starts from
+        if (e == 0) sync_chunk(a, 0, a.head_known ? a.head_off : 0u, a.head_known != 0, clut_sh);
+        return;
+    }
     const Chunk k = chunk_of(a, c);
     uint32_t cnt = 0, exit_bits = 0;
     if (k.walkable) {
@@ -849,7 +858,11 @@ __global__ void __launch_bounds__(kTransfer16Threads, 1) chunk_transfer16_kernel
     for (uint64_t item = (uint64_t)blockIdx.x * kTransfer16Threads + threadIdx.x; item < total; item += (uint64_t)gridDim.x * kTransfer16Threads) {
         const uint32_t idx = (uint32_t)(total - 1u - item);
         const uint32_t c = idx >> s_log2, e = idx & ((1u << s_log2) - 1u);
-        if (c == 0 || e >= n_states) continue;  // chunk 0 is entered at the head: chunk_sync_kernel walks it
+        if (e >= n_states) continue;
+        if (c == 0) {  // chunk 0 is entered at the head of the stream (or at its guess, for a shard): one walk, what the scan starts from
+            if (e == 0) sync_chunk(a, 0, a.head_known ? a.head_off : 0u, a.head_known != 0, clut_sh);
+            continue;
+        }
         const Chunk k = chunk_of(a, c);
         uint32_t cnt = 0, exit_bits = 0;
         if (k.walkable) {
@@ -1165,7 +1178,6 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
         // slowly synchronising codes: the chunks' transfer functions and a scan instead of repair rounds
         uint32_t s_log2 = 1;
         while ((1u << s_log2) < transfer_states) ++s_log2;
-        chunk_sync_kernel<<<1, kChunkThreads, 0, stream>>>(a, 0, 1u);  // chunk 0 from the head (or from its guess, for a shard)
         const uint64_t threads = (uint64_t)n << s_log2;
         if (tune.d_lane_tables && threads >= (uint64_t)tune.num_sms * kTransfer16Threads * 4 &&
             (size_t)tune.max_smem >= kCount16TableBytes + kLutSize * 4u) {
@@ -1182,7 +1194,7 @@ cudaError_t launch_unpack(const UnpackGeometry &g, uint32_t chunk_bytes, const u
         compose_segments_kernel<<<seg_blocks, kSegThreads, 0, stream>>>(a, s_log2, transfer_states, seg_prefix, block_map);
         compose_blocks_kernel<<<1, 1024, 0, stream>>>(seg_blocks, transfer_states, block_map);
         compose_apply_kernel<<<seg_blocks, kSegThreads, 0, stream>>>(a, s_log2, transfer_states, seg_prefix, block_map);
-        if (launches) *launches += 5;
+        if (launches) *launches += 4;
         rounds = 1;
     } else {
         chunk_sync_kernel<<<nb, kChunkThreads, 0, stream>>>(a, 0);
