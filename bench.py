@@ -440,6 +440,8 @@ def run_ours(args, rank, world):
             os.dup2(saved, 1)
             os.close(saved)
     codec = et.Codec(local)
+    if os.environ.get("ET_BENCH_DEBUG"):  # developer switch: ET_TUNE_DEBUG bits (per-phase timing lines on stderr)
+        codec.set_tuning(et._abi.TUNE_DEBUG, int(os.environ["ET_BENCH_DEBUG"]))
     n_total, kind = WORKLOADS[args.workload]
     plan = sharded.ShardPlan(n_total, world, rank)
     n = plan.n_local

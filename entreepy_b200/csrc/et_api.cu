@@ -197,7 +197,7 @@ int pack_dev(et_ctx *ctx, const void *d_in, size_t n, const et_codebook &cb, uin
     const PackScratch ps = pack_scratch_carve(ctx->d_scratch, g.num_tiles);
     int launches = 0;
     ET_CUDA(ctx, launch_pack(g, ctx->d_small + kOffPackTables, wide, cb.max_length, d_body, bit_phase, ps, ctx->d_scratch, sb,
-                             ctx->num_sms, s, &launches, ctx->tune.pack_single_pass != 0));
+                             ctx->num_sms, s, &launches, ctx->tune.pack_single_pass != 0, ctx->tune.pack_bits_ctas));
     ctx->launches += (uint64_t)launches;
     return ET_OK;
 }
@@ -266,6 +266,7 @@ extern "C" int et_ctx_create(int device, et_ctx **out) {
     ok = ok && cudaMalloc(reinterpret_cast<void **>(&ctx->d_small), kSmallBytes) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_small), kSmallBytes, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && unpack_init_device(device, &ctx->tune) == cudaSuccess;
+    ok = ok && pack_init_device(ctx->tune.max_smem, &ctx->tune.pack_bits_ctas) == cudaSuccess;
     ctx->trie = new (std::nothrow) UnpackTrie;
     ok = ok && ctx->trie != nullptr;
     if (const char *v = getenv("ET_LANE_MIN_BYTES")) ctx->tune.lane_min_bytes = atoll(v);  // read once, here
@@ -316,7 +317,7 @@ extern "C" int et_ctx_set_tuning(et_ctx *ctx, int key, long long value) {
     if (!ctx) return ET_ERR_INVALID_ARG;
     switch (key) {
         case ET_TUNE_LANE_MIN_BYTES: ctx->tune.lane_min_bytes = value; return ET_OK;
-        case ET_TUNE_DEBUG: ctx->tune.debug = value != 0; return ET_OK;
+        case ET_TUNE_DEBUG: ctx->tune.debug = (int)value; return ET_OK;  // bit 0: lane decoder timings, bit 1: phases of the sharded calls
         case ET_TUNE_SYNC_WARPS: ctx->tune.sync_warps = (int)value; return ET_OK;
         case ET_TUNE_WRITE_WARPS: ctx->tune.write_warps = (int)value; return ET_OK;
         case ET_TUNE_NO_TRANSFER: ctx->tune.no_transfer = value != 0; return ET_OK;

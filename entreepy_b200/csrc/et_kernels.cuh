@@ -41,9 +41,13 @@ PackScratch pack_scratch_carve(void *base, uint32_t num_tiles);
 
 // d_tables: narrow -> 256 x {code, len} (u32 pairs); wide -> 256 x u64 codes followed by 256 x u8 lengths.
 // max_len: longest code (sizes the bit image of a warp on the narrow path).
+// bits_ctas_per_sm: from pack_init_device() (0: ask the runtime at every call).
 cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint32_t max_len, uint8_t *d_out, uint32_t bit_phase,
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
-                        cudaStream_t stream, int *launches, bool single_pass = false);
+                        cudaStream_t stream, int *launches, bool single_pass = false, int bits_ctas_per_sm = 0);
+// Once per context: lets the pack kernels use all of an SM's shared memory and reads how many CTAs of pass A fit an SM
+// (both used to be asked of the runtime at every call, a few microseconds each with the GPU waiting).
+cudaError_t pack_init_device(int max_smem, int *bits_ctas_per_sm);
 
 // ---------------------------------------------------------------- K3-K5 (chunked self-synchronising decoder)
 constexpr int kSubseqBits = 128;    // a piece: the unit the stream is read in (one 16-byte load)
@@ -80,6 +84,7 @@ struct UnpackTuning {
     int write_warps = 0;            // > 0: warps per CTA of the write walk (default: as many as fit)
     int no_transfer = 0;            // non-zero: slowly synchronising codes take the repair rounds instead of transfer functions
     int pack_single_pass = 0;       // non-zero: the encoder packs in ONE pass with a decoupled look-back (measured slower, see et_pack.cu)
+    int pack_bits_ctas = 0;         // CTAs of pack pass A per SM (pack_init_device)
     void *d_lane_tables = nullptr;  // device-built tables of the lane-interleaved decoder
 };
 cudaError_t unpack_init_device(int device, UnpackTuning *tune);

@@ -903,9 +903,19 @@ PackScratch pack_scratch_carve(void *base, uint32_t num_tiles) {
     return s;
 }
 
+cudaError_t pack_init_device(int max_smem, int *bits_ctas_per_sm) {
+    cudaError_t err = cudaFuncSetAttribute(pack_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (err != cudaSuccess) return err;
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, region_bits_kernel, kPackThreads, 0);
+    if (err != cudaSuccess) return err;
+    *bits_ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+    return cudaSuccess;
+}
+
 cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, uint32_t max_len, uint8_t *d_out, uint32_t bit_phase,
                         const PackScratch &s, void *scratch_base, size_t scratch_bytes, int num_sms,
-                        cudaStream_t stream, int *launches, bool single_pass) {
+                        cudaStream_t stream, int *launches, bool single_pass, int bits_ctas_per_sm) {
     if (g.num_tiles == 0) return cudaSuccess;
     cudaError_t err = cudaSuccess;
     PackArgs a;
@@ -997,8 +1007,9 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         a.group_shift = 10;
         const uint32_t groups = (n_regions + kPrefixGroup - 1) / kPrefixGroup;
         {
-            int per_sm = 0;  // CTAs of 8 warps that fit an SM (32 KB table each, 48 registers per thread: five)
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, region_bits_kernel, kPackThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+            int per_sm = bits_ctas_per_sm;  // CTAs of 8 warps that fit an SM (32 KB table each, 48 registers per thread: five)
+            if (per_sm < 1 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, region_bits_kernel, kPackThreads, 0) != cudaSuccess || per_sm < 1))
+                per_sm = 4;
             unsigned pa_grid = (unsigned)num_sms * (unsigned)per_sm;
             const unsigned need = (n_regions + kWarps - 1) / kWarps;
             if (pa_grid > need) pa_grid = need;
@@ -1007,8 +1018,10 @@ cudaError_t launch_pack(const PackGeometry &g, const void *d_tables, bool wide, 
         region_prefix_kernel<<<groups, kPrefixGroup, 0, stream>>>(a);
         group_scan_kernel<<<1, 1024, 0, stream>>>(a, groups);
         const int smem = kTableBytes + kRunWarps * (int)a.image_words * 4 + kRunWarps * 32;
-        err = cudaFuncSetAttribute(pack_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (err != cudaSuccess) return err;
+        if (bits_ctas_per_sm < 1) {  // no pack_init_device() for this context
+            err = cudaFuncSetAttribute(pack_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (err != cudaSuccess) return err;
+        }
         int per_sm = (227 * 1024) / (smem + 1024);
         if (per_sm > 2) per_sm = 2;  // __launch_bounds__(.., 2)
         if (per_sm < 1) per_sm = 1;

@@ -1016,7 +1016,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
     const uint32_t sync_grid = sync_blocks < (uint32_t)num_sms ? sync_blocks : (uint32_t)num_sms;
     DecArgs &am = const_cast<DecArgs &>(a);
     unsigned long long *d_dbg = nullptr;
-    if (tune.debug) {
+    if (tune.debug & 1) {
         if (cudaMalloc(&d_dbg, 2 * 256 * 35 * 8) == cudaSuccess) cudaMemsetAsync(d_dbg, 0, 2 * 256 * 35 * 8, stream);
     }
     am.dbg = d_dbg;
@@ -1055,7 +1055,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
         // one look at the scratch header: error flags, symbols found, "an entry was wrong", entry and exit of the shard
         if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
         if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
-        if (tune.debug && d_dbg) {
+        if ((tune.debug & 1) && d_dbg) {
             static unsigned long long h[2 * 256 * 35];
             cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost);
             for (int k = 0; k < 2; ++k) {
@@ -1079,7 +1079,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
                 fprintf(stderr, "\n");
             }
         }
-        if (tune.debug)
+        if (tune.debug & 1)
             fprintf(stderr, "[lanes] regions=%u chunks=%u max_sum=%u rounds=%u changed=%u\n", n_regions, a.n_chunks,
                     *reinterpret_cast<const uint32_t *>(h_hdr + 20), rounds, *h_changed);
         if (*h_changed == 0) break;  // every entry was the true one: what the write walk produced stands
@@ -1094,7 +1094,7 @@ static cudaError_t launch_unpack_lanes(const DecArgs &a, uint32_t n_regions, con
             if (launches) *launches += 1;
             if ((err = cudaMemcpyAsync(h_hdr, d_header, 32, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
             if ((err = cudaStreamSynchronize(stream)) != cudaSuccess) return err;
-            if (tune.debug) fprintf(stderr, "[lanes] repair rounds=%u changed=%u\n", rounds, *h_changed);
+            if (tune.debug & 1) fprintf(stderr, "[lanes] repair rounds=%u changed=%u\n", rounds, *h_changed);
             if (*h_changed == 0) break;
             if (rounds > a.n_chunks + 8u) return cudaErrorUnknown;  // cannot happen: each round settles one more chunk
         }

@@ -115,7 +115,7 @@ ET_API uint32_t et_ctx_last_decode_rounds(const et_ctx *ctx);
 /* Tuning knobs of a context (tests and benchmarks; the defaults are what production wants).  The environment
  * variables ET_LANE_MIN_BYTES and ET_DEBUG_LANES seed the first two when the context is created. */
 #define ET_TUNE_LANE_MIN_BYTES 1 /* bodies of at least this many bytes take the lane-interleaved decoder; -1 = default */
-#define ET_TUNE_DEBUG 2          /* non-zero: one line per decode on stderr */
+#define ET_TUNE_DEBUG 2          /* bit 0: lane decoder timings per decode on stderr; bit 1: host time of the phases of a sharded call (rank 0) */
 #define ET_TUNE_SYNC_WARPS 3     /* warps per CTA of the decoder's count walk; 0 = as many as fit */
 #define ET_TUNE_NO_TRANSFER 5     /* non-zero: slowly synchronising codes are decoded with repair rounds (round 1's way) instead of
                                      the scan of per-chunk transfer functions */
