@@ -20,6 +20,7 @@ an oracle-based stand-in to exercise this host logic over gloo.
 """
 from dataclasses import dataclass, field
 
+import ctypes
 import numpy as np
 
 from . import _abi
@@ -290,12 +291,16 @@ class ShardedCodec:
 
     # ------------------------------------------------------------------ body redistribution (setup for decode)
     def decode_ranges(self, body_bytes):
+        cached = getattr(self, "_ranges_of", None)
+        if cached is not None and cached[0] == body_bytes:
+            return cached[1], cached[2]
         cuts = body_cuts(body_bytes, self.plan.world)
         ranges = []
         for r in range(self.plan.world):
             s = max(cuts[r] - LEAD_IN, 0) if r > 0 else 0
             t = min(cuts[r + 1] + LOOK_AHEAD, body_bytes) if r + 1 < self.plan.world else body_bytes
             ranges.append((s, t))
+        self._ranges_of = (body_bytes, cuts, ranges)
         return cuts, ranges
 
     def scatter_body(self, res, t_body):
@@ -378,7 +383,8 @@ class NativeShardedCodec(ShardedCodec):
         p = self.plan
         r = self.codec.encode_sharded_dev(self.ncomm, t_in.data_ptr(), p.n_local, t_out.data_ptr(), t_out.numel(), 0, self.stream)
         self.backend.hist_ms = self.codec.last_stage_ms()[0]
-        res = EncodeResult(total_bytes=int(r.total_bytes), header=bytes(r.header[: r.header_len]), bit_offsets=[0, int(r.body_bytes) * 8],
+        # (string_at: slicing the ctypes array would build a Python list of a thousand ints on every call)
+        res = EncodeResult(total_bytes=int(r.total_bytes), header=ctypes.string_at(ctypes.addressof(r.header), int(r.header_len)), bit_offsets=[0, int(r.body_bytes) * 8],
                            first_byte=int(r.first_byte), local_bytes=int(r.local_bytes), own_lo=int(r.own_lo), own_hi=int(r.own_hi))
         res.bit_offset = int(r.bit_offset)
         res.n_total = int(r.n_total)
